@@ -1,0 +1,54 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE.  Compiles the UNMODIFIED reference sources where they
+# lie (default /root/reference/src/*.cpp; never copied into this repo) together with
+# oracle/ref_driver.cpp into oracle/_ref/libcafe_ref.so.  oracle/_ref/ is git-ignored but travels to
+# the GPU box with the snapshot.  Does not use the reference's own CMake build; config.h is
+# generated here with the constants CMakeLists.txt:10-15,33 would configure.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${CAFE_REF_DIR:-/root/reference}"
+OUT="$HERE/_ref"
+CXX="${CAFE_REF_CXX:-/usr/bin/g++}"   # not $CXX: the image sets it to a wrapper without libgomp.spec
+if [ ! -d "$REF/src" ]; then
+  echo "reference not present at $REF; keeping any prebuilt $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj"
+cat > "$OUT/config.h" <<'CFG'
+#define PROJECT_NAME "CAFE"
+#define PROJECT_VER  "1.1"
+#define PROJECT_VER_MAJOR "1"
+#define PROJECT_VER_MINOR "1"
+#define PROJECT_VER_PATCH ""
+#define BOUNDING_STEP_SIZE 20
+#define MATRIX_SIZE_MULTIPLIER 3.0
+#define MATRIX_EPSILON 5e-6
+#define OPTIMIZER_HIGH_PRECISION 1e-6
+#define OPTIMIZER_LOW_PRECISION  1e-3
+#define PHASED_OPTIMIZER_PHASE1_ATTEMPTS  4
+#define NUM_OPTIMIZER_INITIALIZATION_ATTEMPTS  1
+#define LAMBDA_PERTURBATION_STEP_SIZE  1
+#define HAVE_GETOPT_H 1
+#define LOG_OFFSET 1.0
+#define TRANSCRIPT_RECONSTRUCTION 2
+#define SIMULATOR 3
+#define MATRIX 6
+#define INFERENCE 8
+CFG
+FLAGS=(-std=c++11 -O2 -fopenmp -fPIC -w -fno-access-control -include "$OUT/config.h" -I"$REF/src"
+       -DDOCTEST_CONFIG_DISABLE -DSILENT -DELPP_NO_CHECK_MACROS -DMODEL_GENE_EXPRESSION_LOGS
+       -DOPTIMIZER_STRATEGY=NelderMead -DDISCRETIZATION_RANGE=200 -DMAX_STACK_FAMILY_SIZE=1000)
+objs=()
+pids=()
+for src in "$REF"/src/*.cpp "$HERE/ref_driver.cpp" "$HERE/ref_gpu_model.cpp"; do
+  [ -f "$src" ] || continue
+  obj="$OUT/obj/$(basename "${src%.cpp}").o"
+  objs+=("$obj")
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ]; then
+    "$CXX" "${FLAGS[@]}" -c "$src" -o "$obj" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+"$CXX" -shared -fopenmp -o "$OUT/libcafe_ref.so" "${objs[@]}" -lz -ldl
+echo "built $OUT/libcafe_ref.so"

@@ -1,0 +1,372 @@
+"""ctypes bindings for the two checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``OracleLib``  -> oracle/liboracle.so   (plain-C restatement, oracle/cafe_oracle.c)
+* ``RefLib``     -> oracle/_ref/libcafe_ref.so (the UNMODIFIED reference sources + oracle/ref_driver.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product (cafe5_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libcafe_ref.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_fp = C.POINTER(C.c_float)
+c_up = C.POINTER(C.c_ubyte)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(c_fp)
+
+
+def _up(a):
+    return None if a is None else a.ctypes.data_as(c_up)
+
+
+def build_oracle(force=False):
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "cafe_oracle.c")):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+def build_ref():
+    """Build oracle/_ref/libcafe_ref.so when the reference sources are present; otherwise keep the prebuilt one."""
+    ref_dir = os.environ.get("CAFE_REF_DIR", "/root/reference")
+    if os.path.isdir(os.path.join(ref_dir, "src")):
+        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class FlatTree:
+    """Flattened tree in the reference's reverse level order (see include/cafe_b200.h)."""
+
+    def __init__(self, parent, branch_length, leaf_col, lambda_class, names=None):
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.branch_length = np.ascontiguousarray(branch_length, dtype=np.float64)
+        self.leaf_col = np.ascontiguousarray(leaf_col, dtype=np.int32)
+        self.lambda_class = np.ascontiguousarray(lambda_class, dtype=np.int32)
+        self.names = names
+        self.n_nodes = len(self.parent)
+        self.n_leaves = int((self.leaf_col >= 0).sum())
+
+
+class OracleLib:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.oracle_chooseln.restype = C.c_double
+        L.oracle_chooseln.argtypes = [C.c_int, C.c_int]
+        L.oracle_birthdeath_rate_with_log_alpha.restype = C.c_double
+        L.oracle_birthdeath_rate_with_log_alpha.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+        L.oracle_transition_probability.restype = C.c_double
+        L.oracle_transition_probability.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        L.oracle_matrix.restype = None
+        L.oracle_matrix.argtypes = [C.c_int, C.c_double, C.c_double, c_dp]
+        L.oracle_is_saturated.restype = C.c_int
+        L.oracle_is_saturated.argtypes = [C.c_double, C.c_double]
+        L.oracle_key_lambda.restype = C.c_int64
+        L.oracle_key_lambda.argtypes = [C.c_double]
+        L.oracle_key_branch.restype = C.c_int64
+        L.oracle_key_branch.argtypes = [C.c_double]
+        L.oracle_get_gamma.restype = None
+        L.oracle_get_gamma.argtypes = [C.c_int, C.c_double, c_dp, c_dp]
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_max_threads.restype = C.c_int
+        tree_args = [C.c_int, c_ip, c_dp, c_ip, c_ip]
+        L.oracle_prune.restype = C.c_int
+        L.oracle_prune.argtypes = tree_args + [c_ip, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, c_dp, C.c_double, c_dp]
+        L.oracle_eval_base.restype = C.c_int
+        L.oracle_eval_base.argtypes = tree_args + [c_ip, C.c_long, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,
+                                                   c_dp, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
+        L.oracle_eval_gamma.restype = C.c_int
+        L.oracle_eval_gamma.argtypes = tree_args + [c_ip, C.c_long, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,
+                                                    c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_double, c_dp, c_dp, C.c_int,
+                                                    c_dp, c_dp, c_dp, c_dp, c_up, c_up, C.POINTER(C.c_long), c_dp]
+        L.oracle_reconstruct.restype = C.c_int
+        L.oracle_reconstruct.argtypes = tree_args + [c_ip, C.c_long, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,
+                                                     c_dp, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip, c_dp]
+
+    # scalar helpers
+    def chooseln(self, n, r):
+        return self.lib.oracle_chooseln(n, r)
+
+    def birthdeath(self, s, c, log_alpha, coeff):
+        return self.lib.oracle_birthdeath_rate_with_log_alpha(s, c, log_alpha, coeff)
+
+    def transition(self, lam, t, s, c):
+        return self.lib.oracle_transition_probability(lam, t, s, c)
+
+    def matrix(self, N, lam, t):
+        out = np.empty((N, N), dtype=np.float64)
+        self.lib.oracle_matrix(N, lam, t, _dp(out))
+        return out
+
+    def get_gamma(self, K, alpha):
+        p = np.empty(K)
+        m = np.empty(K)
+        self.lib.oracle_get_gamma(K, alpha, _dp(p), _dp(m))
+        return p, m
+
+    def set_threads(self, n):
+        self.lib.oracle_set_threads(n)
+
+    def max_threads(self):
+        return self.lib.oracle_max_threads()
+
+    @staticmethod
+    def _tree(t):
+        return [t.n_nodes, _ip(t.parent), _dp(t.branch_length), _ip(t.leaf_col), _ip(t.lambda_class)]
+
+    @staticmethod
+    def _em(em):
+        if em is None:
+            return None, 0, 0, None
+        probs, maxcnt = em
+        probs = np.ascontiguousarray(probs, dtype=np.float64)
+        return _dp(probs), probs.shape[0], int(maxcnt), probs
+
+    def prune(self, tree, counts_row, max_family_size, max_root, lambdas, multiplier=1.0, em=None):
+        counts_row = np.ascontiguousarray(counts_row, dtype=np.int32)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        out = np.empty(max_root)
+        emp, emr, emm, _keep = self._em(em)
+        rc = self.lib.oracle_prune(*self._tree(tree), _ip(counts_row), max_family_size, max_root, emp, emr, emm,
+                                   _dp(lambdas), multiplier, _dp(out))
+        if rc:
+            raise RuntimeError("oracle_prune rc=%d" % rc)
+        return out
+
+    def eval_base(self, tree, counts, max_family_size, max_root, prior, lambdas, em=None, want_roots=False):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        F, nl = counts.shape
+        prior = np.ascontiguousarray(prior, dtype=np.float32)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        neg = C.c_double()
+        fam = np.empty(F)
+        roots = np.empty((F, max_root)) if want_roots else None
+        emp, emr, emm, _keep = self._em(em)
+        rc = self.lib.oracle_eval_base(*self._tree(tree), _ip(counts), F, nl, max_family_size, max_root, _fp(prior), len(prior),
+                                       emp, emr, emm, _dp(lambdas), len(lambdas), C.byref(neg), _dp(fam), _dp(roots))
+        if rc:
+            raise RuntimeError("oracle_eval_base rc=%d" % rc)
+        return dict(neg_lnl=neg.value, family_lnl=fam, roots=roots)
+
+    def eval_gamma(self, tree, counts, max_family_size, max_root, prior, lambdas, multipliers, cat_probs,
+                   alpha=1.0, em=None, want_roots=False):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        F, nl = counts.shape
+        K = len(multipliers)
+        prior = np.ascontiguousarray(prior, dtype=np.float32)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        multipliers = np.ascontiguousarray(multipliers, dtype=np.float64)
+        cat_probs = np.ascontiguousarray(cat_probs, dtype=np.float64)
+        neg = C.c_double()
+        nf = C.c_long()
+        cat = np.zeros((F, K))
+        fam = np.zeros(F)
+        post = np.zeros((F, K))
+        sig = np.zeros((F, K), dtype=np.uint8)
+        failed = np.zeros(F, dtype=np.uint8)
+        roots = np.empty((F, K, max_root)) if want_roots else None
+        emp, emr, emm, _keep = self._em(em)
+        rc = self.lib.oracle_eval_gamma(*self._tree(tree), _ip(counts), F, nl, max_family_size, max_root, _fp(prior), len(prior),
+                                        emp, emr, emm, _dp(lambdas), len(lambdas), alpha, _dp(multipliers), _dp(cat_probs), K,
+                                        C.byref(neg), _dp(cat), _dp(fam), _dp(post), _up(sig), _up(failed), C.byref(nf), _dp(roots))
+        if rc:
+            raise RuntimeError("oracle_eval_gamma rc=%d" % rc)
+        return dict(neg_lnl=neg.value, cat_lk=cat, family_lk=fam, posterior=post, significant=sig, failed=failed,
+                    n_failed=nf.value, roots=roots)
+
+    def reconstruct(self, tree, counts, max_family_size, max_root, prior, lambdas, multipliers=None, cat_probs=None):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        F, nl = counts.shape
+        K = 0 if multipliers is None else len(multipliers)
+        KK = max(K, 1)
+        prior = np.ascontiguousarray(prior, dtype=np.float32)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        mu = None if K == 0 else np.ascontiguousarray(multipliers, dtype=np.float64)
+        cp = None if K == 0 else np.ascontiguousarray(cat_probs, dtype=np.float64)
+        cat_states = np.zeros((F, KK, tree.n_nodes), dtype=np.int32)
+        states = np.zeros((F, tree.n_nodes), dtype=np.int32)
+        avg = np.zeros((F, tree.n_nodes))
+        rc = self.lib.oracle_reconstruct(*self._tree(tree), _ip(counts), F, nl, max_family_size, max_root, _fp(prior), len(prior),
+                                         _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K, _ip(cat_states), _ip(states), _dp(avg))
+        if rc:
+            raise RuntimeError("oracle_reconstruct rc=%d" % rc)
+        return dict(cat_states=cat_states, states=states, averaged=avg)
+
+
+class RefLib:
+    """The unmodified reference, via oracle/ref_driver.cpp."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise RuntimeError("oracle/_ref/libcafe_ref.so missing (run oracle/build_ref.sh where /root/reference exists)")
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_birthdeath_rate_with_log_alpha.restype = C.c_double
+        L.ref_birthdeath_rate_with_log_alpha.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+        L.ref_transition_probability.restype = C.c_double
+        L.ref_transition_probability.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        L.ref_chooseln.restype = C.c_double
+        L.ref_chooseln.argtypes = [C.c_double, C.c_double]
+        L.ref_matrix.argtypes = [C.c_int, C.c_double, C.c_double, c_dp]
+        L.ref_is_saturated.argtypes = [C.c_double, C.c_double]
+        L.ref_get_gamma.argtypes = [C.c_int, C.c_double, c_dp, c_dp]
+        L.ref_tree_node_count.argtypes = [C.c_char_p]
+        L.ref_tree_flatten.argtypes = [C.c_char_p, C.c_char_p, c_ip, c_dp, c_ip, c_ip, C.c_char_p, C.c_int]
+        L.ref_ctx_create.restype = C.c_void_p
+        L.ref_ctx_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, c_ip, C.c_long, C.c_int, C.c_int,
+                                     c_dp, C.c_int, c_dp, C.c_int, C.c_int]
+        L.ref_ctx_destroy.argtypes = [C.c_void_p]
+        L.ref_ctx_set_error_model.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int]
+        L.ref_prune.argtypes = [C.c_void_p, C.c_long, c_dp, C.c_int, C.c_double, c_dp]
+        L.ref_eval_base.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp]
+        L.ref_eval_gamma.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, c_up]
+        L.ref_reconstruct_base.argtypes = [C.c_void_p, c_dp, C.c_int, c_ip]
+        L.ref_reconstruct_gamma.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip, c_dp]
+        L.ref_set_threads.argtypes = [C.c_int]
+        L.ref_max_threads.restype = C.c_int
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError("reference: " + self.lib.ref_last_error().decode())
+
+    def birthdeath(self, s, c, log_alpha, coeff):
+        return self.lib.ref_birthdeath_rate_with_log_alpha(s, c, log_alpha, coeff)
+
+    def transition(self, lam, t, s, c):
+        return self.lib.ref_transition_probability(lam, t, s, c)
+
+    def chooseln(self, n, r):
+        return self.lib.ref_chooseln(float(n), float(r))
+
+    def matrix(self, N, lam, t):
+        out = np.empty((N, N))
+        self._check(self.lib.ref_matrix(N, lam, t, _dp(out)))
+        return out
+
+    def get_gamma(self, K, alpha):
+        p = np.empty(K)
+        m = np.empty(K)
+        self.lib.ref_get_gamma(K, alpha, _dp(p), _dp(m))
+        return p, m
+
+    def set_threads(self, n):
+        self.lib.ref_set_threads(n)
+
+    def max_threads(self):
+        return self.lib.ref_max_threads()
+
+    def flatten(self, newick, lambda_newick=None):
+        n = self.lib.ref_tree_node_count(newick.encode())
+        if n < 0:
+            self._check(1)
+        parent = np.empty(n, dtype=np.int32)
+        bl = np.empty(n)
+        is_leaf = np.empty(n, dtype=np.int32)
+        lc = np.empty(n, dtype=np.int32)
+        buf = C.create_string_buffer(1 << 20)
+        self._check(self.lib.ref_tree_flatten(newick.encode(), (lambda_newick or "").encode(), _ip(parent), _dp(bl),
+                                              _ip(is_leaf), _ip(lc), buf, len(buf)))
+        names = buf.value.decode().split("\t")
+        return parent, bl, is_leaf, lc, names
+
+    class Ctx:
+        def __init__(self, ref, newick, species, counts, max_family_size, max_root, prior, lambda_newick=None, em=None):
+            self.ref = ref
+            counts = np.ascontiguousarray(counts, dtype=np.int32)
+            self.F, self.nl = counts.shape
+            prior = np.ascontiguousarray(prior, dtype=np.float64)
+            self.R = max_root
+            self.n_nodes = ref.lib.ref_tree_node_count(newick.encode())
+            emp, emr, emm = None, 0, 0
+            if em is not None:
+                probs = np.ascontiguousarray(em[0], dtype=np.float64)
+                emp, emr, emm = _dp(probs), probs.shape[0], int(em[1])
+            self.h = ref.lib.ref_ctx_create(newick.encode(), (lambda_newick or "").encode(), "\t".join(species).encode(),
+                                            _ip(counts), self.F, max_family_size, max_root, _dp(prior), len(prior),
+                                            emp, emr, emm)
+            if not self.h:
+                ref._check(1)
+
+        def close(self):
+            if self.h:
+                self.ref.lib.ref_ctx_destroy(self.h)
+                self.h = None
+
+        def __del__(self):
+            try:
+                self.close()
+            except Exception:
+                pass
+
+        def set_error_model(self, probs, maxcnt):
+            probs = np.ascontiguousarray(probs, dtype=np.float64)
+            self.ref._check(self.ref.lib.ref_ctx_set_error_model(self.h, _dp(probs), probs.shape[0], int(maxcnt)))
+
+        def prune(self, family, lambdas, multiplier=1.0):
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            out = np.empty(self.R)
+            self.ref._check(self.ref.lib.ref_prune(self.h, family, _dp(lambdas), len(lambdas), multiplier, _dp(out)))
+            return out
+
+        def eval_base(self, lambdas):
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            neg = C.c_double()
+            fam = np.full(self.F, np.nan)
+            self.ref._check(self.ref.lib.ref_eval_base(self.h, _dp(lambdas), len(lambdas), C.byref(neg), _dp(fam)))
+            return dict(neg_lnl=neg.value, family_lnl=fam)
+
+        def eval_gamma(self, lambdas, multipliers, cat_probs):
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            mu = np.ascontiguousarray(multipliers, dtype=np.float64)
+            cp = np.ascontiguousarray(cat_probs, dtype=np.float64)
+            K = len(mu)
+            neg = C.c_double()
+            cat = np.zeros((self.F, K))
+            failed = np.zeros(self.F, dtype=np.uint8)
+            self.ref._check(self.ref.lib.ref_eval_gamma(self.h, _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K,
+                                                        C.byref(neg), _dp(cat), _up(failed)))
+            return dict(neg_lnl=neg.value, cat_lk=cat, failed=failed)
+
+        def reconstruct_base(self, lambdas):
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            st = np.zeros((self.F, self.n_nodes), dtype=np.int32)
+            self.ref._check(self.ref.lib.ref_reconstruct_base(self.h, _dp(lambdas), len(lambdas), _ip(st)))
+            return st
+
+        def reconstruct_gamma(self, lambdas, multipliers, cat_probs):
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            mu = np.ascontiguousarray(multipliers, dtype=np.float64)
+            cp = np.ascontiguousarray(cat_probs, dtype=np.float64)
+            K = len(mu)
+            cs = np.zeros((self.F, K, self.n_nodes), dtype=np.int32)
+            st = np.zeros((self.F, self.n_nodes), dtype=np.int32)
+            avg = np.zeros((self.F, self.n_nodes))
+            self.ref._check(self.ref.lib.ref_reconstruct_gamma(self.h, _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K,
+                                                               _ip(cs), _ip(st), _dp(avg)))
+            return dict(cat_states=cs, states=st, averaged=avg)
+
+    def ctx(self, *a, **k):
+        return RefLib.Ctx(self, *a, **k)

@@ -1,0 +1,363 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// A thin extern "C" driver that is compiled TOGETHER WITH the unmodified reference
+// sources where they lie (/root/reference/src/*.cpp) into oracle/_ref/libcafe_ref.so by
+// oracle/build_ref.sh.  It builds the reference's own objects (clade, gene_family,
+// base_model, gamma_model, error_model, root_equilibrium_distribution) and calls the
+// reference's own functions for the hot path, so tests can pin the C restatement
+// (oracle/cafe_oracle.c) and the CUDA path against the real thing:
+//   matrix_cache::precalculate_matrices / get_matrix      src/matrix_cache.cpp:88-163
+//   birthdeath_rate_with_log_alpha                         src/probability.cpp:104-148
+//   inference_prune                                        src/core.cpp:134-145
+//   base_model::infer_family_likelihoods                   src/base_model.cpp:53-100
+//   gamma_model::infer_family_likelihoods / prune          src/gamma_core.cpp:143-237
+//   base_model/gamma_model::reconstruct_ancestral_states   src/base_model.cpp:133-170, src/gamma_core.cpp:290-339
+//   get_gamma                                              src/gamma.cpp:225-241
+// Built with -fno-access-control so per-family side-channel outputs (model::results,
+// gamma_model::_category_likelihoods) can be read without modifying the reference.
+// No reference source is copied into this repository.
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <set>
+#include <omp.h>
+
+#include "easylogging++.h"
+#include "clade.h"
+#include "gene_family.h"
+#include "lambda.h"
+#include "matrix_cache.h"
+#include "probability.h"
+#include "core.h"
+#include "base_model.h"
+#include "gamma_core.h"
+#include "gamma.h"
+#include "error_model.h"
+#include "root_equilibrium_distribution.h"
+#include "user_data.h"
+#include "io.h"
+#include "gene_family_reconstructor.h"
+#include "optimizer.h"
+#include "optimizer_scorer.h"
+
+INITIALIZE_EASYLOGGINGPP
+
+std::mt19937 randomizer_engine(10);  // the reference's main.cpp seeds from random_device; we seed explicitly
+
+void init_lgamma_cache();
+
+namespace {
+
+bool g_inited = false;
+void ensure_init()
+{
+    if (g_inited) return;
+    init_lgamma_cache();
+    el::Configurations conf;
+    conf.setToDefault();
+    conf.set(el::Level::Global, el::ConfigurationType::Enabled, "false");
+    conf.set(el::Level::Global, el::ConfigurationType::ToFile, "false");
+    conf.set(el::Level::Global, el::ConfigurationType::ToStandardOutput, "false");
+    el::Loggers::reconfigureLogger("default", conf);
+    g_inited = true;
+}
+
+std::vector<std::string> split(const std::string& s, char d)
+{
+    std::vector<std::string> out;
+    std::stringstream ss(s);
+    std::string item;
+    while (std::getline(ss, item, d)) out.push_back(item);
+    return out;
+}
+
+struct ref_ctx {
+    std::unique_ptr<clade> tree;
+    std::unique_ptr<clade> lambda_tree;
+    std::vector<const clade*> order;          // reverse level order
+    int max_family_size = 0, max_root_family_size = 0;
+    std::unique_ptr<error_model> em;
+    user_data ud;
+    input_parameters ui;
+    std::string err;
+};
+
+lambda* make_lambda(ref_ctx* c, const double* lambdas, int n)
+{
+    if (c->lambda_tree) {
+        auto m = c->lambda_tree->get_lambda_index_map();
+        return new multiple_lambda(m, std::vector<double>(lambdas, lambdas + n));
+    }
+    return new single_lambda(lambdas[0]);
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ref_max_threads() { return omp_get_max_threads(); }
+
+double ref_birthdeath_rate_with_log_alpha(int s, int c, double log_alpha, double coeff)
+{
+    ensure_init();
+    return birthdeath_rate_with_log_alpha(s, c, log_alpha, coeff);
+}
+
+double ref_transition_probability(double lambda, double t, int s, int c)
+{
+    ensure_init();
+    return the_probability_of_going_from_parent_fam_size_to_c(lambda, t, s, c);
+}
+
+double ref_chooseln(double n, double r) { ensure_init(); return chooseln(n, r); }
+
+// Full N x N matrix via the reference's cache (so key quantisation applies).  out is row-major [s][c].
+int ref_matrix(int N, double lambda, double t, double* out)
+{
+    ensure_init();
+    try {
+        matrix_cache cache(N);
+        cache.precalculate_matrices(std::vector<double>{lambda}, std::set<double>{t});
+        const matrix* m = cache.get_matrix(t, lambda);
+        for (int s = 0; s < N; ++s)
+            for (int c = 0; c < N; ++c) out[s * N + c] = m->get(s, c);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+int ref_is_saturated(double t, double lambda) { return matrix_cache::is_saturated(t, lambda) ? 1 : 0; }
+
+int ref_get_gamma(int K, double alpha, double* probs, double* multipliers)
+{
+    std::vector<double> f(K), r(K);
+    get_gamma(f, r, alpha);
+    for (int i = 0; i < K; ++i) { probs[i] = f[i]; multipliers[i] = r[i]; }
+    return 0;
+}
+
+// ---- tree flattening: nodes in the reference's reverse level order (src/clade.cpp:69-100) ----
+int ref_tree_node_count(const char* newick)
+{
+    try {
+        std::unique_ptr<clade> t(parse_newick(newick));
+        return int(t->reverse_level_end() - t->reverse_level_begin());
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// names_out: '\t'-joined node names in reverse level order (caller buffer).  lambda_class filled
+// from lambda_newick (0-based) when given, else zeros.
+int ref_tree_flatten(const char* newick, const char* lambda_newick, int* parent, double* branch_length,
+                     int* is_leaf, int* lambda_class, char* names_out, int names_cap)
+{
+    try {
+        std::unique_ptr<clade> t(parse_newick(newick));
+        std::vector<const clade*> order(t->reverse_level_begin(), t->reverse_level_end());
+        std::map<const clade*, int> idx;
+        for (size_t i = 0; i < order.size(); ++i) idx[order[i]] = int(i);
+        std::map<std::string, int> lmap;
+        if (lambda_newick && *lambda_newick) {
+            std::unique_ptr<clade> lt(parse_newick(lambda_newick, true));
+            t->validate_lambda_tree(lt.get());
+            lmap = lt->get_lambda_index_map();
+        }
+        std::string names;
+        for (size_t i = 0; i < order.size(); ++i) {
+            const clade* c = order[i];
+            parent[i] = c->is_root() ? -1 : idx.at(c->get_parent());
+            branch_length[i] = c->get_branch_length();
+            is_leaf[i] = c->is_leaf() ? 1 : 0;
+            lambda_class[i] = lmap.empty() ? 0 : lmap.at(c->get_taxon_name());
+            if (i) names += '\t';
+            names += c->get_taxon_name();
+        }
+        if (int(names.size()) + 1 > names_cap) { g_err = "names buffer too small"; return 2; }
+        std::strcpy(names_out, names.c_str());
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// ---- context ----
+// species: '\t'-joined leaf names giving the column order of counts (F x n_species, row-major).
+// prior: n_prior doubles (float-representable); installed verbatim as the prior's percentage table.
+// error model: em_rows x 3 doubles or NULL.
+void* ref_ctx_create(const char* newick, const char* lambda_newick, const char* species,
+                     const int* counts, long F, int max_family_size, int max_root_family_size,
+                     const double* prior, int n_prior,
+                     const double* em_probs, int em_rows, int em_maxcnt)
+{
+    ensure_init();
+    try {
+        auto c = new ref_ctx();
+        c->tree.reset(parse_newick(newick));
+        if (lambda_newick && *lambda_newick) {
+            c->lambda_tree.reset(parse_newick(lambda_newick, true));
+            c->tree->validate_lambda_tree(c->lambda_tree.get());
+        }
+        c->order.assign(c->tree->reverse_level_begin(), c->tree->reverse_level_end());
+        auto sp = split(species, '\t');
+        c->ud.gene_families.resize(F);
+        for (long f = 0; f < F; ++f) {
+            c->ud.gene_families[f].set_id(std::to_string(f));
+            for (size_t j = 0; j < sp.size(); ++j)
+                c->ud.gene_families[f].set_species_size(sp[j], counts[f * sp.size() + j]);
+        }
+        c->max_family_size = max_family_size;
+        c->max_root_family_size = max_root_family_size;
+        root_equilibrium_distribution p((size_t)std::max(n_prior, 1));
+        p._frequency_percentage.assign(prior, prior + n_prior);
+        c->ud.prior = std::move(p);
+        if (em_probs) {
+            c->em.reset(new error_model());
+            c->em->set_max_family_size(em_maxcnt);
+            for (int i = 0; i < em_rows; ++i)
+                c->em->set_probabilities(i, {em_probs[3 * i], em_probs[3 * i + 1], em_probs[3 * i + 2]});
+        }
+        c->ud.p_tree = c->tree.get();
+        c->ud.max_family_size = max_family_size;
+        c->ud.max_root_family_size = max_root_family_size;
+        return c;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+void ref_ctx_destroy(void* h) { delete (ref_ctx*)h; }
+
+// Replace the error-model rows (the optimiser mutates epsilon every step).
+int ref_ctx_set_error_model(void* h, const double* em_probs, int em_rows, int em_maxcnt)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        c->em.reset(new error_model());
+        c->em->set_max_family_size(em_maxcnt);
+        for (int i = 0; i < em_rows; ++i)
+            c->em->set_probabilities(i, {em_probs[3 * i], em_probs[3 * i + 1], em_probs[3 * i + 2]});
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Root vector (R doubles; index i <-> root size i+1) for one family: inference_prune.
+int ref_prune(void* h, long family, const double* lambdas, int n_lambda, double multiplier, double* out)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        std::unique_ptr<lambda> mult(lam->multiply(multiplier));
+        matrix_cache calc(std::max(c->max_root_family_size, c->max_family_size) + 1);
+        calc.precalculate_matrices(get_lambda_values(mult.get()), c->tree->get_branch_lengths());
+        auto v = inference_prune(c->ud.gene_families[family], calc, lam.get(), c->em.get(), c->tree.get(), multiplier,
+                                 c->max_root_family_size, c->max_family_size);
+        std::copy(v.begin(), v.end(), out);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// base_model::infer_family_likelihoods; family_lnl (F) may be NULL.
+int ref_eval_base(void* h, const double* lambdas, int n_lambda, double* neg_lnl, double* family_lnl)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        base_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, c->em.get());
+        *neg_lnl = m.infer_family_likelihoods(c->ud.prior, lam.get());
+        if (family_lnl && !std::isinf(*neg_lnl))
+            for (size_t i = 0; i < m.results.size(); ++i) family_lnl[i] = m.results[i].posterior_probability;
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Same, but skipping the O(F*U) dedup of the model constructor for timing large samples: not needed,
+// the constructor is outside the timed call below.
+void* ref_base_model_create(void* h, const double* lambdas, int n_lambda)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        lambda* lam = make_lambda(c, lambdas, n_lambda);
+        return new base_model(lam, c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, c->em.get());
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+// gamma_model::infer_family_likelihoods with explicit multipliers / category probabilities.
+// cat_lk: F x K (may be NULL); failed: F bytes (may be NULL), from gamma_model::prune's return value.
+int ref_eval_gamma(void* h, const double* lambdas, int n_lambda, const double* multipliers, const double* cat_probs,
+                   int K, double* neg_lnl, double* cat_lk, unsigned char* failed)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        gamma_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size,
+                      std::vector<double>(cat_probs, cat_probs + K), std::vector<double>(multipliers, multipliers + K), c->em.get());
+        m._alpha = 1.0;  // explicit multipliers were supplied; can_infer only needs alpha >= 0
+        *neg_lnl = m.infer_family_likelihoods(c->ud.prior, lam.get());
+        size_t F = c->ud.gene_families.size();
+        for (size_t i = 0; i < F; ++i) {
+            const auto& v = m._category_likelihoods[i];
+            bool ok = v.size() == size_t(K);
+            if (failed) failed[i] = ok ? 0 : 1;
+            if (cat_lk) for (int k = 0; k < K; ++k) cat_lk[i * K + k] = (k < int(v.size())) ? v[k] : 0.0;
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Pupko reconstruction, base model.  states: F x n_nodes ints in reverse level order (leaves = observed).
+int ref_reconstruct_base(void* h, const double* lambdas, int n_lambda, int* states)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        base_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, c->em.get());
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);  // src/execute.cpp:167
+        std::unique_ptr<reconstruction> rec(m.reconstruct_ancestral_states(c->ud, c->ui, &cache));
+        size_t n = c->order.size();
+        for (size_t f = 0; f < c->ud.gene_families.size(); ++f)
+            for (size_t i = 0; i < n; ++i) states[f * n + i] = rec->get_node_count(c->ud.gene_families[f], c->order[i]);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Pupko reconstruction, gamma model: per-category states (F x K x n_nodes) and rounded weighted
+// average (F x n_nodes, leaves = observed).  averaged_raw (F x n_nodes doubles) may be NULL.
+int ref_reconstruct_gamma(void* h, const double* lambdas, int n_lambda, const double* multipliers,
+                          const double* cat_probs, int K, int* cat_states, int* states, double* averaged_raw)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        gamma_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size,
+                      std::vector<double>(cat_probs, cat_probs + K), std::vector<double>(multipliers, multipliers + K), c->em.get());
+        m._alpha = 1.0;
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+        std::unique_ptr<reconstruction> rec(m.reconstruct_ancestral_states(c->ud, c->ui, &cache));
+        auto g = dynamic_cast<gamma_model_reconstruction*>(rec.get());
+        size_t n = c->order.size();
+        for (size_t f = 0; f < c->ud.gene_families.size(); ++f) {
+            const auto& r = g->_reconstructions.at(c->ud.gene_families[f].id());
+            for (size_t i = 0; i < n; ++i) {
+                const clade* node = c->order[i];
+                states[f * n + i] = rec->get_node_count(c->ud.gene_families[f], node);
+                for (int k = 0; k < K; ++k) {
+                    int v = node->is_leaf() ? c->ud.gene_families[f].get_species_size(node->get_taxon_name())
+                                            : r.category_reconstruction[k].at(node);
+                    cat_states[(f * K + k) * n + i] = v;
+                }
+                if (averaged_raw)
+                    averaged_raw[f * n + i] = node->is_leaf() ? double(states[f * n + i]) : r.reconstruction.at(node);
+            }
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Viterbi branch p-value (src/gene_family_reconstructor.cpp:390-429) restated through the matrix only:
+// kept out; "next" row f2.
+
+}  // extern "C"
