@@ -1,0 +1,88 @@
+"""ctypes binding of libcafe_b200.so (the C ABI in include/cafe_b200.h).
+
+There is no fallback: if the CUDA library is missing or cannot be loaded this module raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcafe_b200.so")
+
+# every symbol include/cafe_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "cafe_b200_create", "cafe_b200_destroy", "cafe_b200_last_error", "cafe_b200_set_prior",
+    "cafe_b200_set_error_model", "cafe_b200_eval_base", "cafe_b200_eval_gamma", "cafe_b200_reconstruct",
+    "cafe_b200_get_matrix", "cafe_b200_matrix_size", "cafe_b200_root_vectors", "cafe_b200_enqueue_eval",
+    "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
+]
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_fp = C.POINTER(C.c_float)
+c_up = C.POINTER(C.c_uint8)
+
+
+class CTree(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("parent", c_ip), ("branch_length", c_dp), ("leaf_col", c_ip),
+                ("lambda_class", c_ip)]
+
+
+_lib = None
+
+
+def load():
+    """Load libcafe_b200.so; raises RuntimeError when it is absent (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libcafe_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.cafe_b200_create.restype = C.c_int
+    L.cafe_b200_create.argtypes = [C.POINTER(CTree), c_ip, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.cafe_b200_destroy.argtypes = [vp]
+    L.cafe_b200_last_error.restype = C.c_char_p
+    L.cafe_b200_last_error.argtypes = [vp]
+    L.cafe_b200_set_prior.argtypes = [vp, c_fp, C.c_int32]
+    L.cafe_b200_set_error_model.argtypes = [vp, c_dp, C.c_int32, C.c_int32]
+    L.cafe_b200_eval_base.argtypes = [vp, c_dp, C.c_int32, c_dp, c_dp]
+    L.cafe_b200_eval_gamma.argtypes = [vp, c_dp, C.c_int32, C.c_double, c_dp, c_dp, C.c_int32,
+                                       c_dp, c_dp, c_dp, c_dp, c_up, c_up, C.POINTER(C.c_int64)]
+    L.cafe_b200_reconstruct.argtypes = [vp, c_dp, C.c_int32, c_dp, c_dp, C.c_int32, c_ip, c_ip, c_dp]
+    L.cafe_b200_get_matrix.argtypes = [vp, C.c_double, C.c_double, c_dp]
+    L.cafe_b200_matrix_size.restype = C.c_int32
+    L.cafe_b200_matrix_size.argtypes = [vp]
+    L.cafe_b200_root_vectors.argtypes = [vp, c_dp, C.c_int32, C.c_double, c_dp]
+    L.cafe_b200_enqueue_eval.argtypes = [vp, c_dp, C.c_int32, C.c_double, c_dp, c_dp, C.c_int32]
+    L.cafe_b200_fetch_result.argtypes = [vp, c_dp, C.POINTER(C.c_int64)]
+    L.cafe_b200_stream.restype = vp
+    L.cafe_b200_stream.argtypes = [vp]
+    L.cafe_b200_last_stats.argtypes = [vp, c_ip, c_ip, c_fp, c_fp]
+    L.cafe_b200_unique_families.restype = C.c_int64
+    L.cafe_b200_unique_families.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def fp(a):
+    return None if a is None else a.ctypes.data_as(c_fp)
+
+
+def up(a):
+    return None if a is None else a.ctypes.data_as(c_up)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

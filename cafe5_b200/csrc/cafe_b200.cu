@@ -1,0 +1,851 @@
+// cafe_b200.cu -- host side of libcafe_b200.so: context, per-evaluation key planning, launches, C ABI.
+// See include/cafe_b200.h for the boundary and the reference interfaces each entry point replaces.
+#include "../../include/cafe_b200.h"
+#include "kernels.cuh"
+#include "pupko.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace cafe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError { std::string msg; };
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw CudaError{buf_};                                                                 \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n, bool zero = false)
+    {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+        if (zero) CK(cudaMemset(p, 0, n * sizeof(T)));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct KeyPlan {
+    std::vector<MatParam> params;          // one per distinct matrix key
+    std::vector<int32_t> mat_of;           // [K][n_nodes]
+};
+
+}  // namespace
+
+struct cafe_b200_ctx {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // tree (host copies)
+    int n_nodes = 0;
+    std::vector<int32_t> parent, leaf_col, lambda_class;
+    std::vector<double> branch_length;
+    int n_lambda_classes = 1;
+    int S = 0, R = 0, N = 0, max_family_size = 0;
+
+    // families
+    int64_t F = 0, U = 0, U_stride = 0;
+    int n_species = 0;
+    std::vector<int32_t> counts;           // F x n_species (host copy, for leaf states)
+    std::vector<int64_t> f2u;
+
+    // schedule
+    std::vector<Step> steps;
+    std::vector<StepChild> children;
+    int n_slots = 0;
+    std::vector<int32_t> leaf_row_of_node; // row in counts_t for leaf nodes
+
+    // tiling choice
+    int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
+
+    // prior / error model
+    bool have_prior = false;
+    std::vector<float> prior;
+    bool have_em = false;
+    int em_rows = 0, em_maxcnt = 0;
+
+    // device buffers
+    DevBuf<int32_t> d_counts_t, d_mat_of;
+    DevBuf<int64_t> d_f2u;
+    DevBuf<Step> d_steps;
+    DevBuf<StepChild> d_children;
+    DevBuf<double> d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
+    DevBuf<uint8_t> d_ok;
+    DevBuf<MatParam> d_params;
+    DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
+    DevBuf<uint8_t> d_significant, d_failed;
+    // pupko
+    DevBuf<uint16_t> d_argmax;
+    DevBuf<int32_t> d_states, d_leaf_row, d_states_f, d_cat_states_f;
+    DevBuf<double> d_avg_f;
+    int lg_n = 0;
+
+    // pinned staging
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    double* h_result = nullptr;
+
+    // stats
+    int last_launches = 0, last_mats = 0;
+    bool stats_valid = false;
+
+    void* stage(size_t bytes)
+    {
+        if (bytes > h_stage_cap) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr;
+            h_stage_cap = 0;
+            CK(cudaMallocHost(&h_stage, bytes));
+            h_stage_cap = bytes;
+        }
+        return h_stage;
+    }
+};
+
+namespace {
+
+// ---- schedule: post-order over internal nodes, heavier subtree first, so few vectors are live ----
+void build_schedule(cafe_b200_ctx* c)
+{
+    const int n = c->n_nodes;
+    std::vector<std::vector<int>> kids(n);
+    for (int i = n - 1; i >= 0; --i)
+        if (c->parent[i] >= 0) kids[c->parent[i]].push_back(i);   // decreasing index == reference descendant order
+    std::vector<int> need(n, 0);
+    for (int i = 0; i < n; ++i) {                                 // children precede parents
+        if (c->leaf_col[i] >= 0) continue;
+        std::vector<int> sub;
+        for (int k : kids[i]) if (c->leaf_col[k] < 0) sub.push_back(need[k]);
+        std::sort(sub.rbegin(), sub.rend());
+        int best = 1;
+        for (size_t j = 0; j < sub.size(); ++j) best = std::max(best, sub[j] + (int)j);
+        need[i] = std::max(best, (int)sub.size() + 0) ;
+        if (need[i] < 1) need[i] = 1;
+    }
+    std::vector<int> order;
+    std::vector<int> stack{n - 1};
+    // iterative post-order with children visited by decreasing need
+    std::vector<int> state(n, 0);
+    std::vector<std::vector<int>> visit(n);
+    for (int i = 0; i < n; ++i) {
+        for (int k : kids[i]) if (c->leaf_col[k] < 0) visit[i].push_back(k);
+        std::stable_sort(visit[i].begin(), visit[i].end(), [&](int a, int b) { return need[a] > need[b]; });
+    }
+    while (!stack.empty()) {
+        int v = stack.back();
+        if (state[v] < (int)visit[v].size()) stack.push_back(visit[v][state[v]++]);
+        else { order.push_back(v); stack.pop_back(); }
+    }
+    // slot assignment with reuse
+    std::vector<int> slot_of(n, -1);
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    c->steps.clear();
+    c->children.clear();
+    for (int v : order) {
+        Step st{};
+        st.node = v;
+        st.is_root = c->parent[v] < 0;
+        st.child_begin = (int)c->children.size();
+        st.n_children = (int)kids[v].size();
+        int s;
+        if (!free_slots.empty()) { s = free_slots.back(); free_slots.pop_back(); }
+        else s = n_slots++;
+        st.out_slot = s;
+        slot_of[v] = s;
+        for (int k : kids[v]) {
+            StepChild ch{};
+            ch.node = k;
+            ch.leaf_row = c->leaf_col[k] >= 0 ? c->leaf_row_of_node[k] : -1;
+            ch.slot = c->leaf_col[k] >= 0 ? -1 : slot_of[k];
+            c->children.push_back(ch);
+        }
+        c->steps.push_back(st);
+        for (int k : kids[v]) if (c->leaf_col[k] < 0) free_slots.push_back(slot_of[k]);
+    }
+    std::vector<int> step_of(n, -1);
+    for (size_t i = 0; i < c->steps.size(); ++i) step_of[c->steps[i].node] = (int)i;
+    for (auto& st : c->steps) st.parent_step = c->parent[st.node] < 0 ? -1 : step_of[c->parent[st.node]];
+    c->n_slots = n_slots;
+}
+
+void choose_tiling(cafe_b200_ctx* c)
+{
+    // rows per pass BM = 16*TM, TM in 8..13; minimise padded rows, then passes
+    int bestTM = 11, bestTiles = 1 << 30, bestPad = 1 << 30;
+    for (int tm = 8; tm <= 13; ++tm) {
+        int bm = 16 * tm;
+        int tiles = (c->N + bm - 1) / bm;
+        int pad = tiles * bm;
+        if (pad < bestPad || (pad == bestPad && tiles < bestTiles)) { bestPad = pad; bestTiles = tiles; bestTM = tm; }
+    }
+    c->TM = bestTM;
+    c->n_mtiles = bestTiles;
+    c->LD = bestPad;
+}
+
+template <int TM, int TN>
+void launch_prune_t(cafe_b200_ctx* c, PruneParams& p)
+{
+    using Cfg = PruneCfg<TM, TN>;
+    size_t smem = Cfg::smem_bytes(c->S);
+    CK(cudaFuncSetAttribute(prune_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prune_kernel<TM, TN><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p);
+    CK(cudaGetLastError());
+}
+
+template <int TN>
+void launch_prune_tn(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TM) {
+    case 8: launch_prune_t<8, TN>(c, p); break;
+    case 9: launch_prune_t<9, TN>(c, p); break;
+    case 10: launch_prune_t<10, TN>(c, p); break;
+    case 11: launch_prune_t<11, TN>(c, p); break;
+    case 12: launch_prune_t<12, TN>(c, p); break;
+    default: launch_prune_t<13, TN>(c, p); break;
+    }
+}
+
+void launch_prune(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TN) {
+    case 4: launch_prune_tn<4>(c, p); break;
+    case 2: launch_prune_tn<2>(c, p); break;
+    default: launch_prune_tn<1>(c, p); break;
+    }
+}
+
+// Column-tile width by problem size: wide tiles amortise matrix traffic, narrow tiles fill the SMs
+void choose_columns(cafe_b200_ctx* c, int K)
+{
+    int tn = 4;
+    while (tn > 1) {
+        int64_t tiles = ((c->U + 16 * tn - 1) / (16 * tn)) * K;
+        if (tiles >= 2 * (int64_t)c->n_sms) break;
+        tn >>= 1;
+    }
+    c->TN = tn;
+    int bn = 16 * tn;
+    c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+    int64_t tiles = (int64_t)c->n_col_tiles * K;
+    c->grid = (int)std::min<int64_t>(tiles, c->n_sms);
+}
+
+// ---- key planning (matrix_cache_key, src/matrix_cache.h:44-63; lambda::multiply, src/lambda.h:45-48,76-84) ----
+KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* multipliers, int K)
+{
+    KeyPlan kp;
+    kp.mat_of.assign((size_t)K * c->n_nodes, 0);
+    std::map<std::pair<long, long>, int> index;
+    for (int k = 0; k < K; ++k) {
+        for (int i = 0; i < c->n_nodes; ++i) {
+            if (c->parent[i] < 0) continue;
+            double lam = lambdas[c->lambda_class[i]] * multipliers[k];
+            long kl = long(lam * 1000000000);
+            long kt = long(c->branch_length[i] * 1000);
+            auto key = std::make_pair(kl, kt);
+            auto it = index.find(key);
+            int id;
+            if (it == index.end()) {
+                id = (int)kp.params.size();
+                index.emplace(key, id);
+                double ql = double(kl) / 1000000000.0;
+                double qt = double(kt) / 1000.0;
+                double alpha = ql * qt / (1 + ql * qt);
+                double coeff = 1 - 2 * alpha;
+                MatParam mp{};
+                mp.coeff = coeff;
+                mp.zero = !(coeff > 0 && coeff != 1);   // covers is_saturated (coeff < 0)
+                mp.log_alpha = mp.zero ? 0.0 : std::log(alpha);
+                kp.params.push_back(mp);
+            } else id = it->second;
+            kp.mat_of[(size_t)k * c->n_nodes + i] = id;
+        }
+    }
+    return kp;
+}
+
+void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp)
+{
+    size_t n_mats = kp.params.size();
+    size_t arena = n_mats * (size_t)c->LD * c->LD;
+    if (arena > c->d_arena.cap) {
+        c->d_arena.reserve(arena + arena / 4);
+        CK(cudaMemsetAsync(c->d_arena.p, 0, c->d_arena.cap * sizeof(double), c->stream));   // zero padding once
+    }
+    c->d_params.reserve(n_mats);
+    c->d_mat_of.reserve(kp.mat_of.size());
+    size_t b1 = n_mats * sizeof(MatParam), b2 = kp.mat_of.size() * sizeof(int32_t);
+    CK(cudaStreamSynchronize(c->stream));   // the staging buffer may still feed a previous async copy
+    char* h = (char*)c->stage(b1 + b2);
+    memcpy(h, kp.params.data(), b1);
+    memcpy(h + b1, kp.mat_of.data(), b2);
+    CK(cudaMemcpyAsync(c->d_params.p, h, b1, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_mat_of.p, h + b1, b2, cudaMemcpyHostToDevice, c->stream));
+}
+
+void launch_matrices(cafe_b200_ctx* c, int n_mats)
+{
+    dim3 grid(c->N, n_mats);
+    matrix_gen_kernel<<<grid, 192, c->lg_n * sizeof(double), c->stream>>>(c->d_params.p, c->d_lg.p, c->lg_n, c->N, c->LD, c->d_arena.p);
+    CK(cudaGetLastError());
+}
+
+PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
+{
+    choose_columns(c, K);
+    const int bn = 16 * c->TN, bm = 16 * c->TM;
+    PruneParams p{};
+    p.steps = c->d_steps.p;
+    p.children = c->d_children.p;
+    p.mat_of = c->d_mat_of.p;
+    p.arena = c->d_arena.p;
+    p.counts_t = c->d_counts_t.p;
+    p.em = c->have_em ? c->d_em.p : nullptr;
+    p.prior_d = c->d_prior.p;
+    p.logprior = c->d_logprior.p;
+    p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
+    c->d_scratch.reserve((size_t)c->grid * c->n_slots * p.slot_stride);
+    p.scratch = c->d_scratch.p;
+    c->d_best.reserve((size_t)K * c->U_stride);
+    c->d_ok.reserve((size_t)K * c->U_stride);
+    p.out_best = c->d_best.p;
+    p.out_ok = c->d_ok.p;
+    p.out_roots = nullptr;
+    p.U = c->U;
+    p.U_stride = c->U_stride;
+    p.n_steps = (int)c->steps.size();
+    p.n_nodes = c->n_nodes;
+    p.n_slots = c->n_slots;
+    p.LD = c->LD; p.S = c->S; p.R = c->R; p.N = c->N; p.K = K;
+    p.n_col_tiles = c->n_col_tiles;
+    p.n_mtiles = c->n_mtiles;
+    p.em_rows = c->em_rows;
+    p.mode = mode;
+    return p;
+}
+
+bool lambdas_valid(const double* lambdas, int n)
+{
+    // single_lambda::is_valid: lambda > 0 (lambda.h:58-60); multiple_lambda::is_valid: none < 0 (lambda.cpp:59-62)
+    if (n == 1) return lambdas[0] > 0;
+    for (int i = 0; i < n; ++i) if (lambdas[i] < 0) return false;
+    return true;
+}
+
+// Enqueue one evaluation (matrices + prune + finish) on the stream.  Returns false (and sets the
+// host-side infinite result) when the parameters are rejected before any kernel runs.
+bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double alpha, const double* multipliers,
+                  const double* cat_probs, int n_cat)
+{
+    if (!c->have_prior) throw CudaError{"STATE: set_prior must be called before eval"};
+    if (n_lambda < c->n_lambda_classes) throw CudaError{"ARG: fewer lambdas than lambda classes in the tree"};
+    c->stats_valid = false;
+    c->last_launches = 0;
+    c->last_mats = 0;
+    const bool gamma = n_cat > 0;
+    const int K = gamma ? n_cat : 1;
+    static const double one = 1.0;
+    if (!gamma) multipliers = &one;
+    bool ok = lambdas_valid(lambdas, n_lambda);
+    if (ok && gamma) {
+        // gamma_model::can_infer (gamma_core.cpp:123-141)
+        if (alpha < 0) ok = false;
+        double maxlam = *std::max_element(lambdas, lambdas + n_lambda);
+        double maxbl = 0;
+        for (int i = 0; i < c->n_nodes; ++i) if (c->branch_length[i] > 0) maxbl = std::max(maxbl, c->branch_length[i]);
+        double a = maxlam * maxbl / (1 + maxlam * maxbl);
+        if ((1 - 2 * a) < 0) ok = false;
+    }
+    if (!ok) return false;
+
+    KeyPlan kp = plan_keys(c, lambdas, multipliers, K);
+    upload_plan(c, kp);
+    const int n_mats = (int)kp.params.size();
+    c->last_mats = n_mats;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    launch_matrices(c, n_mats);
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    PruneParams p = base_params(c, K, gamma ? MODE_GAMMA : MODE_BASE);
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    launch_prune(c, p);
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    const int nb = (int)((c->F + FIN_THREADS - 1) / FIN_THREADS);
+    c->d_partial.reserve(nb);
+    c->d_partial_fail.reserve(nb);
+    c->d_result.reserve(2);
+    c->d_family_lnl.reserve(c->F);
+    if (!gamma) {
+        finish_base_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_best.p, c->d_f2u.p, c->F, c->d_family_lnl.p, c->d_partial.p);
+        CK(cudaGetLastError());
+        final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, nullptr, nb, c->d_result.p);
+    } else {
+        c->d_cat_lk.reserve((size_t)c->F * K);
+        c->d_posterior.reserve((size_t)c->F * K);
+        c->d_significant.reserve((size_t)c->F * K);
+        c->d_family_lk.reserve(c->F);
+        c->d_failed.reserve(c->F);
+        c->d_cat_probs.reserve(K);
+        CK(cudaMemcpyAsync(c->d_cat_probs.p, cat_probs, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        finish_gamma_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_best.p, c->d_ok.p, c->U_stride, c->d_f2u.p, c->F, K,
+                                                               c->d_cat_probs.p, c->d_cat_lk.p, c->d_family_lk.p, c->d_posterior.p,
+                                                               c->d_significant.p, c->d_failed.p, c->d_partial.p, c->d_partial_fail.p);
+        CK(cudaGetLastError());
+        final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, c->d_partial_fail.p, nb, c->d_result.p);
+    }
+    CK(cudaGetLastError());
+    c->last_launches = 4;
+    c->stats_valid = true;
+    return true;
+}
+
+template <typename T>
+void d2h(cafe_b200_ctx* c, T* dst, const T* src, size_t n)
+{
+    if (dst && n) CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+}
+
+int fail(cafe_b200_ctx* c, const CudaError& e)
+{
+    int code = CAFE_B200_ERR_CUDA;
+    std::string m = e.msg;
+    if (m.rfind("ARG: ", 0) == 0) { code = CAFE_B200_ERR_ARG; m = m.substr(5); }
+    else if (m.rfind("RANGE: ", 0) == 0) { code = CAFE_B200_ERR_RANGE; m = m.substr(7); }
+    else if (m.rfind("STATE: ", 0) == 0) { code = CAFE_B200_ERR_STATE; m = m.substr(7); }
+    if (c) c->err = m; else g_create_error = m;
+    return code;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                     int32_t max_family_size, int32_t max_root_family_size, int32_t device, cafe_b200_ctx** out)
+{
+    if (out) *out = nullptr;
+    cafe_b200_ctx* c = nullptr;
+    try {
+        if (!tree || !counts || !out || n_families <= 0 || n_species <= 0 || max_family_size < 1 || max_root_family_size < 1)
+            throw CudaError{"ARG: null or non-positive argument"};
+        const int n = tree->n_nodes;
+        if (n < 3 || !tree->parent || !tree->branch_length || !tree->leaf_col || !tree->lambda_class)
+            throw CudaError{"ARG: tree needs at least a root and two children"};
+        if (tree->parent[n - 1] != -1) throw CudaError{"ARG: the root must be the last node (reverse level order)"};
+        int n_leaves = 0, max_class = 0;
+        for (int i = 0; i < n; ++i) {
+            if (i < n - 1 && (tree->parent[i] <= i || tree->parent[i] >= n))
+                throw CudaError{"ARG: nodes must be in reverse level order (children before parents)"};
+            if (tree->leaf_col[i] >= n_species) throw CudaError{"ARG: leaf_col out of range"};
+            if (tree->leaf_col[i] >= 0) ++n_leaves;
+            if (tree->lambda_class[i] < 0) throw CudaError{"ARG: negative lambda class"};
+            max_class = std::max(max_class, tree->lambda_class[i]);
+        }
+        std::vector<int> nkids(n, 0);
+        for (int i = 0; i < n - 1; ++i) nkids[tree->parent[i]]++;
+        for (int i = 0; i < n; ++i) {
+            if ((tree->leaf_col[i] >= 0) != (nkids[i] == 0)) throw CudaError{"ARG: leaf_col must be >= 0 exactly for childless nodes"};
+            if (tree->leaf_col[i] >= 0 && i == n - 1) throw CudaError{"ARG: root cannot be a leaf"};
+        }
+        int dev_count = 0;
+        if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+            throw CudaError{"no CUDA device available: libcafe_b200 has no CPU fallback"};
+        if (device < 0 || device >= dev_count) throw CudaError{"ARG: device ordinal out of range"};
+
+        c = new cafe_b200_ctx();
+        c->device = device;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        c->n_sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(&c->h_result, 2 * sizeof(double)));
+
+        c->n_nodes = n;
+        c->parent.assign(tree->parent, tree->parent + n);
+        c->leaf_col.assign(tree->leaf_col, tree->leaf_col + n);
+        c->lambda_class.assign(tree->lambda_class, tree->lambda_class + n);
+        c->branch_length.assign(tree->branch_length, tree->branch_length + n);
+        c->n_lambda_classes = max_class + 1;
+        c->max_family_size = max_family_size;
+        c->S = max_family_size + 1;
+        c->R = max_root_family_size;
+        c->N = std::max(max_root_family_size, max_family_size) + 1;   // base_model.cpp:65, gamma_core.cpp:185
+        choose_tiling(c);
+        if (PruneCfg<13, 4>::smem_bytes(c->S) > (size_t)prop.sharedMemPerBlockOptin && PruneCfg<13, 1>::smem_bytes(c->S) > (size_t)prop.sharedMemPerBlockOptin)
+            throw CudaError{"RANGE: max_family_size too large for the shared-memory resident child vector"};
+
+        // ---- families: validate, build the reference list (identical count vectors pruned once) ----
+        c->F = n_families;
+        c->n_species = n_species;
+        c->counts.assign(counts, counts + (size_t)n_families * n_species);
+        std::vector<int> leaf_nodes;
+        c->leaf_row_of_node.assign(n, -1);
+        for (int i = 0; i < n; ++i)
+            if (c->leaf_col[i] >= 0) { c->leaf_row_of_node[i] = (int)leaf_nodes.size(); leaf_nodes.push_back(i); }
+        std::unordered_map<std::string, int64_t> seen;
+        seen.reserve((size_t)n_families * 2);
+        c->f2u.resize(n_families);
+        std::vector<int64_t> uniq;
+        std::string key((size_t)n_leaves * sizeof(int32_t), '\0');
+        for (int64_t f = 0; f < n_families; ++f) {
+            const int32_t* row = counts + (size_t)f * n_species;
+            for (int j = 0; j < n_leaves; ++j) {
+                int32_t v = row[c->leaf_col[leaf_nodes[j]]];
+                if (v < 0 || v > max_family_size) throw CudaError{"RANGE: a count is negative or exceeds max_family_size"};
+                memcpy(&key[(size_t)j * sizeof(int32_t)], &v, sizeof v);
+            }
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (int64_t)uniq.size()).first;
+                uniq.push_back(f);
+            }
+            c->f2u[f] = it->second;
+        }
+        c->U = (int64_t)uniq.size();
+        c->U_stride = (c->U + 63) / 64 * 64;
+        std::vector<int32_t> counts_t((size_t)n_leaves * c->U_stride, 0);
+        for (int64_t u = 0; u < c->U; ++u) {
+            const int32_t* row = counts + (size_t)uniq[u] * n_species;
+            for (int j = 0; j < n_leaves; ++j) counts_t[(size_t)j * c->U_stride + u] = row[c->leaf_col[leaf_nodes[j]]];
+        }
+        c->d_counts_t.reserve(counts_t.size());
+        CK(cudaMemcpy(c->d_counts_t.p, counts_t.data(), counts_t.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->d_f2u.reserve(n_families);
+        CK(cudaMemcpy(c->d_f2u.p, c->f2u.data(), (size_t)n_families * sizeof(int64_t), cudaMemcpyHostToDevice));
+
+        build_schedule(c);
+        c->d_steps.reserve(c->steps.size());
+        CK(cudaMemcpy(c->d_steps.p, c->steps.data(), c->steps.size() * sizeof(Step), cudaMemcpyHostToDevice));
+        c->d_children.reserve(c->children.size());
+        CK(cudaMemcpy(c->d_children.p, c->children.data(), c->children.size() * sizeof(StepChild), cudaMemcpyHostToDevice));
+
+        // lgamma table with the HOST libm, the same values the reference caches (probability.cpp:69-80)
+        c->lg_n = 2 * c->N + 2;
+        std::vector<double> lg(c->lg_n);
+        for (int i = 0; i < c->lg_n; ++i) lg[i] = std::lgamma((double)i);
+        c->d_lg.reserve(lg.size());
+        CK(cudaMemcpy(c->d_lg.p, lg.data(), lg.size() * sizeof(double), cudaMemcpyHostToDevice));
+        *out = c;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) {
+        int code = fail(nullptr, e);
+        if (c) cafe_b200_destroy(c);
+        return code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        if (c) cafe_b200_destroy(c);
+        return CAFE_B200_ERR_ARG;
+    }
+}
+
+int cafe_b200_destroy(cafe_b200_ctx* c)
+{
+    if (!c) return CAFE_B200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->d_counts_t.release(); c->d_mat_of.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
+    c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
+    c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
+    c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
+    c->d_partial.release(); c->d_partial_fail.release(); c->d_result.release(); c->d_roots.release();
+    c->d_significant.release(); c->d_failed.release(); c->d_argmax.release(); c->d_states.release();
+    c->d_leaf_row.release(); c->d_states_f.release(); c->d_cat_states_f.release(); c->d_avg_f.release();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CAFE_B200_OK;
+}
+
+const char* cafe_b200_last_error(const cafe_b200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int cafe_b200_set_prior(cafe_b200_ctx* c, const float* prior, int32_t n)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!prior || n < 0) throw CudaError{"ARG: null prior"};
+        CK(cudaSetDevice(c->device));
+        c->prior.assign(prior, prior + n);
+        // Inference weights root index j by compute(j), j < R (base_model.cpp:84, gamma_core.cpp:156);
+        // Pupko uses compute(j) for j < min(max_family_size, R) + 1 (gene_family_reconstructor.cpp:65,146).
+        const int len = std::max(c->R, std::min(c->max_family_size, c->R) + 1);
+        std::vector<double> pd(len), lp(len);
+        for (int j = 0; j < len; ++j) {
+            pd[j] = j < n ? (double)prior[j] : 0.0;           // float widened, as `double eq_freq = prior.compute(j)`
+            lp[j] = std::log(pd[j]);                          // host libm, as std::log(eq_freq)
+        }
+        c->d_prior.reserve(len);
+        c->d_logprior.reserve(len);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(c->d_prior.p, pd.data(), len * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_logprior.p, lp.data(), len * sizeof(double), cudaMemcpyHostToDevice));
+        c->have_prior = true;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_set_error_model(cafe_b200_ctx* c, const double* probs, int32_t rows, int32_t max_cnt)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(c->device));
+        if (!probs) { c->have_em = false; return CAFE_B200_OK; }
+        if (rows < 1) throw CudaError{"ARG: error model needs at least one row"};
+        c->d_em.reserve((size_t)rows * 3);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(c->d_em.p, probs, (size_t)rows * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        c->em_rows = rows;
+        c->em_maxcnt = max_cnt;
+        c->have_em = true;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_eval_base(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double* neg_lnl, double* family_lnl)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || n_lambda < 1 || !neg_lnl) throw CudaError{"ARG: null argument"};
+        CK(cudaSetDevice(c->device));
+        if (!enqueue_eval(c, lambdas, n_lambda, 0.0, nullptr, nullptr, 0)) {
+            *neg_lnl = std::numeric_limits<double>::infinity();
+            return CAFE_B200_OK;
+        }
+        d2h(c, c->h_result, c->d_result.p, 2);
+        d2h(c, family_lnl, c->d_family_lnl.p, (size_t)c->F);
+        CK(cudaStreamSynchronize(c->stream));
+        *neg_lnl = c->h_result[0];
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_eval_gamma(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double alpha,
+                         const double* multipliers, const double* cat_probs, int32_t n_cat,
+                         double* neg_lnl, double* cat_lk, double* family_lk, double* posterior,
+                         uint8_t* significant, uint8_t* failed, int64_t* n_failed)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || n_lambda < 1 || !neg_lnl || !multipliers || !cat_probs || n_cat < 1) throw CudaError{"ARG: null argument"};
+        CK(cudaSetDevice(c->device));
+        if (n_failed) *n_failed = 0;
+        if (!enqueue_eval(c, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat)) {
+            *neg_lnl = std::numeric_limits<double>::infinity();
+            return CAFE_B200_OK;
+        }
+        const size_t FK = (size_t)c->F * n_cat;
+        d2h(c, c->h_result, c->d_result.p, 2);
+        d2h(c, cat_lk, c->d_cat_lk.p, FK);
+        d2h(c, family_lk, c->d_family_lk.p, (size_t)c->F);
+        d2h(c, posterior, c->d_posterior.p, FK);
+        d2h(c, significant, c->d_significant.p, FK);
+        d2h(c, failed, c->d_failed.p, (size_t)c->F);
+        CK(cudaStreamSynchronize(c->stream));
+        *neg_lnl = c->h_result[0];
+        if (n_failed) *n_failed = (int64_t)c->h_result[1];
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double alpha,
+                           const double* multipliers, const double* cat_probs, int32_t n_cat)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(c->device));
+        if (!enqueue_eval(c, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat))
+            throw CudaError{"ARG: parameters rejected before launch (invalid lambda / alpha / saturated)"};
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_fetch_result(cafe_b200_ctx* c, double* neg_lnl, int64_t* n_failed)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(c->device));
+        d2h(c, c->h_result, c->d_result.p, 2);
+        CK(cudaStreamSynchronize(c->stream));
+        if (neg_lnl) *neg_lnl = c->h_result[0];
+        if (n_failed) *n_failed = (int64_t)c->h_result[1];
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+void* cafe_b200_stream(cafe_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matrices, float* ms_matrices, float* ms_prune)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!c->stats_valid) throw CudaError{"STATE: no evaluation has been launched"};
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        CK(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
+        if (n_launches) *n_launches = c->last_launches;
+        if (n_matrices) *n_matrices = c->last_mats;
+        if (ms_matrices) *ms_matrices = a;
+        if (ms_prune) *ms_prune = b;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int64_t cafe_b200_unique_families(const cafe_b200_ctx* c) { return c ? c->U : 0; }
+int32_t cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->N : 0; }
+
+int cafe_b200_get_matrix(cafe_b200_ctx* c, double lambda, double branch_length, double* out)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!out) throw CudaError{"ARG: null output"};
+        CK(cudaSetDevice(c->device));
+        // one-key plan through the same quantisation as an evaluation
+        cafe_b200_ctx tmp_tree;   // only the fields plan_keys reads
+        tmp_tree.n_nodes = 2;
+        tmp_tree.parent = {1, -1};
+        tmp_tree.lambda_class = {0, 0};
+        tmp_tree.branch_length = {branch_length, 0.0};
+        const double one = 1.0;
+        KeyPlan kp = plan_keys(&tmp_tree, &lambda, &one, 1);
+        // NB: matrix_cache::get_matrix does not refuse lambda <= 0; neither do we.
+        kp.mat_of.assign((size_t)c->n_nodes, 0);
+        upload_plan(c, kp);
+        launch_matrices(c, 1);
+        std::vector<double> pt((size_t)c->LD * c->LD);
+        CK(cudaMemcpyAsync(pt.data(), c->d_arena.p, pt.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int s = 0; s < c->N; ++s)
+            for (int ch = 0; ch < c->N; ++ch) out[(size_t)s * c->N + ch] = pt[(size_t)ch * c->LD + s];
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_root_vectors(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double multiplier, double* out)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || !out || n_lambda < c->n_lambda_classes) throw CudaError{"ARG: bad argument"};
+        if (!c->have_prior) throw CudaError{"STATE: set_prior must be called before eval"};
+        CK(cudaSetDevice(c->device));
+        KeyPlan kp = plan_keys(c, lambdas, &multiplier, 1);
+        upload_plan(c, kp);
+        launch_matrices(c, (int)kp.params.size());
+        PruneParams p = base_params(c, 1, MODE_ROOTS);
+        c->d_roots.reserve((size_t)c->U * c->R);
+        p.out_roots = c->d_roots.p;
+        launch_prune(c, p);
+        std::vector<double> roots((size_t)c->U * c->R);
+        CK(cudaMemcpyAsync(roots.data(), c->d_roots.p, roots.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int64_t f = 0; f < c->F; ++f)
+            memcpy(out + (size_t)f * c->R, roots.data() + (size_t)c->f2u[f] * c->R, c->R * sizeof(double));
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda,
+                          const double* multipliers, const double* cat_probs, int32_t n_cat,
+                          int32_t* cat_states, int32_t* states, double* averaged)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || n_lambda < c->n_lambda_classes || !states) throw CudaError{"ARG: bad argument"};
+        if (n_cat > 0 && (!multipliers || !cat_probs)) throw CudaError{"ARG: gamma reconstruction needs multipliers and cat_probs"};
+        if (!c->have_prior) throw CudaError{"STATE: set_prior must be called before reconstruct"};
+        CK(cudaSetDevice(c->device));
+        const int K = n_cat > 0 ? n_cat : 1;
+        static const double one = 1.0;
+        const double* mult = n_cat > 0 ? multipliers : &one;
+        KeyPlan kp = plan_keys(c, lambdas, mult, K);
+        upload_plan(c, kp);
+        launch_matrices(c, (int)kp.params.size());
+
+        choose_columns(c, K);
+        PupkoParams p{};
+        const int bn = 16 * c->TN, bm = 16 * c->TM;
+        p.steps = c->d_steps.p;
+        p.children = c->d_children.p;
+        p.mat_of = c->d_mat_of.p;
+        p.arena = c->d_arena.p;
+        p.counts_t = c->d_counts_t.p;
+        p.prior_d = c->d_prior.p;
+        p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
+        c->d_scratch.reserve((size_t)c->grid * c->n_slots * p.slot_stride);
+        p.scratch = c->d_scratch.p;
+        p.n_steps = (int)c->steps.size();
+        p.arg_stride = (int64_t)c->n_mtiles * bm * bn;
+        c->d_argmax.reserve((size_t)c->grid * p.n_steps * p.arg_stride);
+        p.argmax = c->d_argmax.p;
+        c->d_states.reserve((size_t)K * c->U_stride * c->n_nodes);
+        p.states = c->d_states.p;
+        p.U = c->U; p.U_stride = c->U_stride;
+        p.n_nodes = c->n_nodes; p.n_slots = c->n_slots;
+        p.LD = c->LD; p.S = c->S; p.R = c->R; p.N = c->N; p.K = K;
+        p.root_len = std::min(c->max_family_size, c->R) + 1;
+        p.n_col_tiles = c->n_col_tiles; p.n_mtiles = c->n_mtiles;
+        launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p);
+        CK(cudaGetLastError());
+        const int n = c->n_nodes;
+        const size_t Fn = (size_t)c->F * n;
+        c->d_cat_probs.reserve(K);
+        static const double one_prob = 1.0;
+        CK(cudaMemcpyAsync(c->d_cat_probs.p, n_cat > 0 ? cat_probs : &one_prob, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->d_leaf_row.reserve(n);
+        CK(cudaMemcpyAsync(c->d_leaf_row.p, c->leaf_row_of_node.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        c->d_states_f.reserve(Fn);
+        if (cat_states) c->d_cat_states_f.reserve(Fn * K);
+        if (averaged) c->d_avg_f.reserve(Fn);
+        const int nb = (int)((Fn + 255) / 256);
+        expand_states_kernel<<<nb, 256, 0, c->stream>>>(c->d_states.p, c->d_f2u.p, c->d_counts_t.p, c->d_leaf_row.p, c->d_cat_probs.p,
+                                                        c->F, c->U_stride, n, K, n_cat > 0 ? 1 : 0,
+                                                        cat_states ? c->d_cat_states_f.p : nullptr, c->d_states_f.p,
+                                                        averaged ? c->d_avg_f.p : nullptr);
+        CK(cudaGetLastError());
+        d2h(c, states, c->d_states_f.p, Fn);
+        d2h(c, cat_states, c->d_cat_states_f.p, Fn * K);
+        d2h(c, averaged, c->d_avg_f.p, Fn);
+        CK(cudaStreamSynchronize(c->stream));
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+}  // extern "C"

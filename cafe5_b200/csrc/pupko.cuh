@@ -1,0 +1,241 @@
+// pupko.cuh -- Pupko joint ancestral reconstruction on the device (sm_100a).
+// Reference: src/gene_family_reconstructor.cpp:30-190 (up-pass with argmax table C, root pick with the
+// prior, traceback), src/gamma_core.cpp:271-288,351-357 (per-category passes, weighted average, round).
+// Same persistent-CTA tiling as prune_kernel: a CTA owns BN unique families of one category and walks
+// the whole tree; the (x, +) contraction is replaced by (x, max/argmax) with j scanned ASCENDING inside
+// each thread so that the reference's strict '>' tie-break (first maximum wins) is reproduced exactly.
+#pragma once
+#include "kernels.cuh"
+
+namespace cafe {
+
+struct PupkoParams {
+    const Step* steps;
+    const StepChild* children;
+    const int32_t* mat_of;      // [K][n_nodes]
+    const double* arena;
+    const int32_t* counts_t;
+    const double* prior_d;      // [>= root_len]
+    double* scratch;            // [grid][n_slots][slot_stride]  L vectors
+    uint16_t* argmax;           // [grid][n_steps][arg_stride]   C tables of the tile in flight
+    int32_t* states;            // [K][U_stride][n_nodes] reconstructed states of internal nodes
+    int64_t U, U_stride, slot_stride, arg_stride;
+    int32_t n_steps, n_nodes, n_slots;
+    int32_t LD, S, R, N, K, root_len;
+    int32_t n_col_tiles, n_mtiles;
+};
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(PRUNE_THREADS, 1)
+pupko_kernel(const PupkoParams p)
+{
+    constexpr int BM = 16 * TM, BN = 16 * TN, BK = PRUNE_BK, STAGES = PRUNE_STAGES;
+    extern __shared__ __align__(16) double smem[];
+    const int kpad = (p.S + BK - 1) / BK * BK;
+    double* Ms = smem;                                   // [kpad][BN]  prod_children L_child[j]
+    double* As = smem + (size_t)kpad * BN;               // [STAGES][BK][BM]
+    int32_t* st_s = reinterpret_cast<int32_t*>(As + (size_t)STAGES * BK * BM);   // [n_steps][BN] traceback states
+
+    const int tid = threadIdx.x;
+    const int tn = tid & 15, tm = tid >> 4;
+    const int n_tiles = p.K * p.n_col_tiles;
+    double* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * p.slot_stride;
+    uint16_t* const my_arg = p.argmax + (size_t)blockIdx.x * p.n_steps * p.arg_stride;
+    const int n_chunks = kpad / BK;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int k = tile / p.n_col_tiles;
+        const int64_t col0 = (int64_t)(tile % p.n_col_tiles) * BN;
+        const int32_t* mat_of = p.mat_of + (size_t)k * p.n_nodes;
+
+        for (int st = 0; st < p.n_steps; ++st) {
+            const Step sp = p.steps[st];
+            // ---- M[j][col] = prod over children (descendant order) of L_child[j][col] ----
+            __syncthreads();
+            for (int ci = 0; ci < sp.n_children; ++ci) {
+                const StepChild ch = p.children[sp.child_begin + ci];
+                if (ch.leaf_row >= 0) {
+                    // reconstruct_leaf_node (:30-46): L[j] = P(j -> obs) = PT[obs][j]; one warp per column, j coalesced
+                    const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
+                    for (int c = tid >> 5; c < BN; c += PRUNE_THREADS / 32) {
+                        int64_t u = col0 + c;
+                        if (u >= p.U) u = p.U - 1;
+                        const int obs = p.counts_t[(size_t)ch.leaf_row * p.U_stride + u];
+                        const double* __restrict__ r = PT + (size_t)obs * p.LD;
+                        for (int j = tid & 31; j < kpad; j += 32) {
+                            const double l = j < p.S ? __ldg(r + j) : 0.0;
+                            Ms[(size_t)j * BN + c] = ci == 0 ? l : __dmul_rn(Ms[(size_t)j * BN + c], l);
+                        }
+                    }
+                } else {
+                    const double* __restrict__ src = my_scratch + (size_t)ch.slot * p.slot_stride;
+                    for (int idx = tid; idx < kpad * BN; idx += PRUNE_THREADS) {
+                        const double l = (idx / BN) < p.S ? src[idx] : 0.0;
+                        Ms[idx] = ci == 0 ? l : __dmul_rn(Ms[idx], l);
+                    }
+                }
+                __syncthreads();
+            }
+
+            if (sp.is_root) {
+                // reconstruct_root_node (:48-76): argmax_{1 <= j < root_len} M[j] * prior(j), strict '>' from -1
+                if (tid < BN) {
+                    double best = -1.0;
+                    int arg = 0;
+                    for (int j = 1; j < p.root_len; ++j) {
+                        const double val = __dmul_rn(Ms[(size_t)j * BN + tid], p.prior_d[j]);
+                        if (val > best) { best = val; arg = j; }
+                    }
+                    st_s[st * BN + tid] = arg;
+                }
+                continue;
+            }
+
+            // reconstruct_internal_node (:78-114): L[i] = max_j M[j] * P(i -> j), C[i] = first argmax
+            const double* __restrict__ PT = p.arena + (size_t)mat_of[sp.node] * p.LD * p.LD;
+            double* const out_slot = my_scratch + (size_t)sp.out_slot * p.slot_stride;
+            uint16_t* const out_arg = my_arg + (size_t)st * p.arg_stride;
+            for (int mt = 0; mt < p.n_mtiles; ++mt) {
+                const int m0 = mt * BM;
+                double best[TM][TN];
+                int arg[TM][TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) { best[i][j] = -1.0; arg[i][j] = 0; }
+                if (mt > 0) __syncthreads();
+                auto load_chunk = [&](int chunk) {
+                    if (chunk < n_chunks) {
+                        double* dst = As + (size_t)(chunk % STAGES) * BK * BM;
+                        const double* __restrict__ g = PT + (size_t)chunk * BK * p.LD + m0;
+                        for (int idx = tid; idx < BK * BM / 2; idx += PRUNE_THREADS) {
+                            const int kk = idx / (BM / 2), mm = (idx % (BM / 2)) * 2;
+                            cp_async16(dst + kk * BM + mm, g + (size_t)kk * p.LD + mm);
+                        }
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int s = 0; s < STAGES - 1; ++s) load_chunk(s);
+                for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                    cp_async_wait<STAGES - 2>();
+                    __syncthreads();
+                    load_chunk(chunk + STAGES - 1);
+                    const double* a_s = As + (size_t)(chunk % STAGES) * BK * BM + tm;
+                    const double* b_s = Ms + (size_t)chunk * BK * BN;
+#pragma unroll
+                    for (int kk = 0; kk < BK; ++kk) {
+                        const int jj = chunk * BK + kk;
+                        double a[TM], b[TN];
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) a[i] = a_s[kk * BM + i * 16];
+#pragma unroll
+                        for (int j = 0; j < TN; ++j) b[j] = b_s[kk * BN + col_of<TN>(tn, j)];
+#pragma unroll
+                        for (int i = 0; i < TM; ++i)
+#pragma unroll
+                            for (int j = 0; j < TN; ++j) {
+                                const double val = __dmul_rn(b[j], a[i]);   // value * matrix->get(i, j)
+                                if (val > best[i][j]) { best[i][j] = val; arg[i][j] = jj; }
+                            }
+                    }
+                }
+                cp_async_wait<0>();
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        const size_t o = (size_t)(m0 + i * 16 + tm) * BN + col_of<TN>(tn, j);
+                        out_slot[o] = best[i][j];
+                        out_arg[o] = (uint16_t)arg[i][j];
+                    }
+            }
+        }
+        // ---- traceback (:173-188): parents were scheduled after their children, so walk the steps backwards
+        __syncthreads();
+        if (tid < BN) {
+            const int64_t u = col0 + tid;
+            for (int st = p.n_steps - 1; st >= 0; --st) {
+                const Step sp = p.steps[st];
+                int s;
+                if (sp.is_root) s = st_s[st * BN + tid];
+                else {
+                    const int ps = st_s[sp.parent_step * BN + tid];
+                    s = my_arg[(size_t)st * p.arg_stride + (size_t)ps * BN + tid];
+                    st_s[st * BN + tid] = s;
+                }
+                if (u < p.U) p.states[((size_t)k * p.U_stride + u) * p.n_nodes + sp.node] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int TM, int TN>
+inline size_t pupko_smem(int S, int n_steps)
+{
+    return PruneCfg<TM, TN>::smem_bytes(S) + sizeof(int32_t) * (size_t)n_steps * 16 * TN;
+}
+
+template <int TM, int TN>
+inline void launch_pupko_t(int grid, int S, cudaStream_t stream, const PupkoParams& p)
+{
+    size_t smem = pupko_smem<TM, TN>(S, p.n_steps);
+    cudaFuncSetAttribute(pupko_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pupko_kernel<TM, TN><<<grid, PRUNE_THREADS, smem, stream>>>(p);
+}
+
+template <int TN>
+inline void launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const PupkoParams& p)
+{
+    switch (TM) {
+    case 8: launch_pupko_t<8, TN>(grid, S, stream, p); break;
+    case 9: launch_pupko_t<9, TN>(grid, S, stream, p); break;
+    case 10: launch_pupko_t<10, TN>(grid, S, stream, p); break;
+    case 11: launch_pupko_t<11, TN>(grid, S, stream, p); break;
+    case 12: launch_pupko_t<12, TN>(grid, S, stream, p); break;
+    default: launch_pupko_t<13, TN>(grid, S, stream, p); break;
+    }
+}
+
+inline void launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p)
+{
+    switch (TN) {
+    case 4: launch_pupko_tn<4>(TM, grid, S, stream, p); break;
+    case 2: launch_pupko_tn<2>(TM, grid, S, stream, p); break;
+    default: launch_pupko_tn<1>(TM, grid, S, stream, p); break;
+    }
+}
+
+// Expand unique -> family, fill leaves with observed counts, average the categories
+// (get_weighted_averages, gamma_core.cpp:271-288: val = sum_k p_k * state_k from 0.0, then round, :356).
+__global__ void __launch_bounds__(256)
+expand_states_kernel(const int32_t* __restrict__ st_u, const int64_t* __restrict__ f2u, const int32_t* __restrict__ counts_t,
+                     const int32_t* __restrict__ leaf_row, const double* __restrict__ cat_probs,
+                     int64_t F, int64_t U_stride, int n_nodes, int K, int gamma,
+                     int32_t* __restrict__ cat_states, int32_t* __restrict__ states, double* __restrict__ averaged)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= F * n_nodes) return;
+    const int64_t f = idx / n_nodes;
+    const int i = (int)(idx % n_nodes);
+    const int64_t u = f2u[f];
+    if (leaf_row[i] >= 0) {
+        const int32_t v = counts_t[(size_t)leaf_row[i] * U_stride + u];
+        states[idx] = v;
+        if (averaged) averaged[idx] = (double)v;
+        if (cat_states) for (int k = 0; k < K; ++k) cat_states[((size_t)f * K + k) * n_nodes + i] = v;
+        return;
+    }
+    double val = 0.0;
+    int32_t last = 0;
+    for (int k = 0; k < K; ++k) {
+        last = st_u[((size_t)k * U_stride + u) * n_nodes + i];
+        if (cat_states) cat_states[((size_t)f * K + k) * n_nodes + i] = last;
+        val = __dadd_rn(val, __dmul_rn(cat_probs[k], (double)last));
+    }
+    if (!gamma) { states[idx] = last; if (averaged) averaged[idx] = (double)last; }
+    else { states[idx] = (int32_t)round(val); if (averaged) averaged[idx] = val; }
+}
+
+}  // namespace cafe

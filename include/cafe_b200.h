@@ -1,0 +1,141 @@
+/* cafe_b200.h -- C ABI of the B200-native CAFE5 likelihood hot path (libcafe_b200.so).
+ *
+ * Drop-in boundary (reference paths relative to /root/reference):
+ *   model::infer_family_likelihoods(prior, lambda)        src/core.h:174
+ *     base_model  implementation                          src/base_model.cpp:53-100
+ *     gamma_model implementation                          src/gamma_core.cpp:168-237
+ *   model::reconstruct_ancestral_states(...)              src/core.h:182
+ *     base / gamma implementations                        src/base_model.cpp:133-170, src/gamma_core.cpp:290-339
+ * Everything at or below those calls (matrix_cache, birthdeath_rate_with_log_alpha,
+ * inference_prune / compute_node_probability, root-prior weighting, gamma mixture,
+ * error-model leaf emission, Pupko reconstruction) runs on the GPU behind this header;
+ * everything above (CLI, model classes, scorers, Nelder-Mead) stays on the host.
+ * INTEGRATION.md shows the `class gpu_model : public model` shim that binds these entry points
+ * into the unmodified reference.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns a status (0 = OK) and
+ *     cafe_b200_last_error() describes the last failure of that context (or of create).
+ *   - numerical failure is NOT an error: invalid lambda / saturated / underflowed families yield
+ *     neg_lnl = +inf exactly as the reference returns -log(0) (base_model.cpp:56-60,
+ *     gamma_core.cpp:174-178,216-225).
+ *   - caller owns every output buffer; NULL means "not wanted".
+ *   - one context per host thread / per GPU; a context is bound to one CUDA device.
+ *   - there is no CPU fallback: create fails with CAFE_B200_ERR_CUDA when no device is usable.
+ *
+ * Tree layout: nodes in the reference's reverse level order (src/clade.cpp:69-100): children
+ * precede parents, the root is the LAST node; the reference's descendant order of a node is
+ * DEcreasing node index (products over children are formed in that order, probability.cpp:209-218).
+ */
+#ifndef CAFE_B200_H
+#define CAFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cafe_b200_ctx cafe_b200_ctx;
+
+enum {
+    CAFE_B200_OK = 0,
+    CAFE_B200_ERR_ARG = 1,     /* malformed argument (tree order, sizes, NULL where required) */
+    CAFE_B200_ERR_CUDA = 2,    /* CUDA runtime failure or no usable device */
+    CAFE_B200_ERR_RANGE = 3,   /* a count exceeds max_family_size / state space too large for the kernels */
+    CAFE_B200_ERR_STATE = 4    /* call sequence error (e.g. eval before set_prior) */
+};
+
+/* Flattened species tree; replaces `const clade*` (src/clade.h) at the boundary. */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t* parent;        /* [n_nodes] parent index, -1 for the root (must be node n_nodes-1) */
+    const double* branch_length;  /* [n_nodes] clade::get_branch_length(); root's own length ignored */
+    const int32_t* leaf_col;      /* [n_nodes] column of `counts` for a leaf, -1 for internal nodes */
+    const int32_t* lambda_class;  /* [n_nodes] 0-based lambda class of the node (lambda tree, src/lambda.cpp:32-40); all 0 for a single lambda */
+} cafe_b200_tree;
+
+/* Replaces model::model (src/core.cpp:60-71): borrows nothing, copies the tree and the count table
+ * (gene_family::get_species_size, src/gene_family.cpp:38-45) to the device, builds the identical-family
+ * reference list (build_reference_list, src/base_model.cpp:27-51).
+ * counts: [n_families x n_species] row-major.  max_family_size / max_root_family_size as derived in
+ * src/user_data.cpp:40-48.  device: CUDA ordinal. */
+int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                     int32_t max_family_size, int32_t max_root_family_size, int32_t device, cafe_b200_ctx** out);
+
+int cafe_b200_destroy(cafe_b200_ctx* ctx);
+
+/* Last error text of ctx (ctx == NULL: of the last failed create on this thread). */
+const char* cafe_b200_last_error(const cafe_b200_ctx* ctx);
+
+/* Root prior table: prior[j] = root_equilibrium_distribution::compute(j) (returns float,
+ * src/root_equilibrium_distribution.h:40, .cpp:81-87); 0 beyond n. */
+int cafe_b200_set_prior(cafe_b200_ctx* ctx, const float* prior, int32_t n);
+
+/* Error model (src/error_model.cpp:52-57 get_probs; consumed at leaves, src/probability.cpp:187-198):
+ * probs[rows x 3] = P(deviation -1, 0, +1 | observed size); sizes >= rows use the last row.  Call
+ * again whenever epsilon changes (error_model::replace_epsilons).  probs == NULL disables it. */
+int cafe_b200_set_error_model(cafe_b200_ctx* ctx, const double* probs, int32_t rows, int32_t max_cnt);
+
+/* base_model::infer_family_likelihoods (src/base_model.cpp:53-100).
+ * lambdas[n_lambda]: value per lambda class.  neg_lnl: -sum_f max_j[log L_f(j) + log prior(j)].
+ * family_lnl[n_families] (optional): model::results[f].posterior_probability. */
+int cafe_b200_eval_base(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda,
+                        double* neg_lnl, double* family_lnl);
+
+/* gamma_model::infer_family_likelihoods (src/gamma_core.cpp:168-237) with the K multipliers and
+ * category probabilities produced on the host by get_gamma (src/gamma.cpp:225-241); alpha is only
+ * used for can_infer (gamma_core.cpp:123-141).
+ * cat_lk[F x K]: gamma_model::_category_likelihoods ; family_lk[F]; posterior[F x K];
+ * significant[F x K] (posterior > 0.95); failed[F] (a category's root vector summed to 0,
+ * gamma_core.cpp:151); n_failed: count of failed families (neg_lnl = +inf when > 0). */
+int cafe_b200_eval_gamma(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, double alpha,
+                         const double* multipliers, const double* cat_probs, int32_t n_cat,
+                         double* neg_lnl, double* cat_lk, double* family_lk, double* posterior,
+                         uint8_t* significant, uint8_t* failed, int64_t* n_failed);
+
+/* Pupko joint reconstruction (src/gene_family_reconstructor.cpp:30-190) for the base model (n_cat == 0)
+ * or per gamma category followed by the weighted average and rounding (src/gamma_core.cpp:271-288,351-357).
+ * cat_states[F x max(n_cat,1) x n_nodes], states[F x n_nodes] (leaves = observed counts),
+ * averaged[F x n_nodes] (optional, un-rounded). */
+int cafe_b200_reconstruct(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda,
+                          const double* multipliers, const double* cat_probs, int32_t n_cat,
+                          int32_t* cat_states, int32_t* states, double* averaged);
+
+/* Test hooks ------------------------------------------------------------------------------- */
+
+/* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after
+ * the reference's quantisation (src/matrix_cache.h:44-63).  out: [N x N] row-major [parent][child],
+ * N = max(max_root_family_size, max_family_size) + 1. */
+int cafe_b200_get_matrix(cafe_b200_ctx* ctx, double lambda, double branch_length, double* out);
+int32_t cafe_b200_matrix_size(const cafe_b200_ctx* ctx);
+
+/* inference_prune (src/core.cpp:134-145) root vectors: out[F x R], index i <-> root size i+1,
+ * for lambda * multiplier. */
+int cafe_b200_root_vectors(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, double multiplier,
+                           double* out);
+
+/* Measurement hooks ------------------------------------------------------------------------ */
+
+/* Device-resident step for bench.py: runs exactly the kernels of eval_gamma / eval_base
+ * (n_cat == 0) on the context's stream WITHOUT the final device->host copies or a host sync.
+ * The scalar result stays on the device and is fetched with cafe_b200_fetch_result. */
+int cafe_b200_enqueue_eval(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, double alpha,
+                           const double* multipliers, const double* cat_probs, int32_t n_cat);
+int cafe_b200_fetch_result(cafe_b200_ctx* ctx, double* neg_lnl, int64_t* n_failed);
+
+/* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
+void* cafe_b200_stream(cafe_b200_ctx* ctx);
+
+/* Kernel accounting for the last eval: launches issued, and CUDA-event milliseconds of the
+ * matrix-generation and pruning kernels (valid after a synchronising call). */
+int cafe_b200_last_stats(cafe_b200_ctx* ctx, int32_t* n_launches, int32_t* n_matrices,
+                         float* ms_matrices, float* ms_prune);
+
+/* Number of distinct count vectors actually pruned (the reference list's unique entries). */
+int64_t cafe_b200_unique_families(const cafe_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAFE_B200_H */
