@@ -16,6 +16,7 @@ SYMBOLS = [
     "cafe_b200_set_error_model", "cafe_b200_eval_base", "cafe_b200_eval_gamma", "cafe_b200_reconstruct",
     "cafe_b200_get_matrix", "cafe_b200_matrix_size", "cafe_b200_root_vectors", "cafe_b200_enqueue_eval",
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
+    "cafe_b200_measure_fp64_peak",
 ]
 
 c_dp = C.POINTER(C.c_double)
@@ -64,6 +65,7 @@ def load():
     L.cafe_b200_last_stats.argtypes = [vp, c_ip, c_ip, c_fp, c_fp]
     L.cafe_b200_unique_families.restype = C.c_int64
     L.cafe_b200_unique_families.argtypes = [vp]
+    L.cafe_b200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, c_dp]
     _lib = L
     return L
 

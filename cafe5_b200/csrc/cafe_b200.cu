@@ -3,10 +3,13 @@
 #include "../../include/cafe_b200.h"
 #include "kernels.cuh"
 #include "pupko.cuh"
+#include "prune_dmma.cuh"
+#include "peak.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -89,6 +92,9 @@ struct cafe_b200_ctx {
 
     // tiling choice
     int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
+    bool use_dmma = true;      // FP64 tensor-core contraction (default); CAFE_B200_PRUNE=dfma selects the DFMA kernel
+    int TNW = 4, dmma_stages = 4;
+    size_t smem_optin = 0;
 
     // prior / error model
     bool have_prior = false;
@@ -248,6 +254,59 @@ void launch_prune(cafe_b200_ctx* c, PruneParams& p)
     }
 }
 
+template <int TMW, int TNW>
+void launch_dmma_t(cafe_b200_ctx* c, PruneParams& p)
+{
+    using Cfg = DmmaCfg<TMW, TNW>;
+    size_t smem = Cfg::smem_bytes(c->dmma_stages);
+    CK(cudaFuncSetAttribute(prune_dmma_kernel<TMW, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prune_dmma_kernel<TMW, TNW><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p, c->dmma_stages);
+    CK(cudaGetLastError());
+}
+
+template <int TNW>
+void launch_dmma_tn(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TM) {
+    case 8: launch_dmma_t<8, TNW>(c, p); break;
+    case 9: launch_dmma_t<9, TNW>(c, p); break;
+    case 10: launch_dmma_t<10, TNW>(c, p); break;
+    case 11: launch_dmma_t<11, TNW>(c, p); break;
+    case 12: launch_dmma_t<12, TNW>(c, p); break;
+    default: launch_dmma_t<13, TNW>(c, p); break;
+    }
+}
+
+void launch_dmma(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TNW) {
+    case 4: launch_dmma_tn<4>(c, p); break;
+    case 2: launch_dmma_tn<2>(c, p); break;
+    default: launch_dmma_tn<1>(c, p); break;
+    }
+}
+
+// DMMA kernel: column tile BN = 32*TNW; wide tiles halve the matrix traffic per FMA, narrow tiles fill the SMs
+int choose_columns_dmma(cafe_b200_ctx* c, int K)
+{
+    int tnw = 4;
+    while (tnw > 1) {
+        int64_t tiles = ((c->U + 32 * tnw - 1) / (32 * tnw)) * K;
+        if (tiles >= 2 * (int64_t)c->n_sms) break;
+        tnw >>= 1;
+    }
+    c->TNW = tnw;
+    const int bn = 32 * tnw, bm = 16 * c->TM;
+    const size_t stage = sizeof(double) * (size_t)DM_BK * (bm + 4 + bn + 4);
+    int stages = (int)(c->smem_optin / stage);
+    c->dmma_stages = stages > 4 ? 4 : stages;
+    if (c->dmma_stages < 2) throw CudaError{"RANGE: state space too large for the pruning pipeline"};
+    c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+    int64_t tiles = (int64_t)c->n_col_tiles * K;
+    c->grid = (int)std::min<int64_t>(tiles, c->n_sms);
+    return bn;
+}
+
 // Column-tile width by problem size: wide tiles amortise matrix traffic, narrow tiles fill the SMs
 void choose_columns(cafe_b200_ctx* c, int K)
 {
@@ -326,8 +385,10 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
 
 PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
 {
-    choose_columns(c, K);
-    const int bn = 16 * c->TN, bm = 16 * c->TM;
+    int bn;
+    if (c->use_dmma) bn = choose_columns_dmma(c, K);
+    else { choose_columns(c, K); bn = 16 * c->TN; }
+    const int bm = 16 * c->TM;
     PruneParams p{};
     p.steps = c->d_steps.p;
     p.children = c->d_children.p;
@@ -401,7 +462,7 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
     CK(cudaEventRecord(c->ev[1], c->stream));
     PruneParams p = base_params(c, K, gamma ? MODE_GAMMA : MODE_BASE);
     CK(cudaEventRecord(c->ev[2], c->stream));
-    launch_prune(c, p);
+    if (c->use_dmma) launch_dmma(c, p); else launch_prune(c, p);
     CK(cudaEventRecord(c->ev[3], c->stream));
     const int nb = (int)((c->F + FIN_THREADS - 1) / FIN_THREADS);
     c->d_partial.reserve(nb);
@@ -492,6 +553,8 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         c->n_sms = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        if (const char* e = std::getenv("CAFE_B200_PRUNE")) c->use_dmma = std::string(e) != "dfma";
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&c->h_result, 2 * sizeof(double)));
@@ -507,8 +570,8 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->R = max_root_family_size;
         c->N = std::max(max_root_family_size, max_family_size) + 1;   // base_model.cpp:65, gamma_core.cpp:185
         choose_tiling(c);
-        if (PruneCfg<13, 4>::smem_bytes(c->S) > (size_t)prop.sharedMemPerBlockOptin && PruneCfg<13, 1>::smem_bytes(c->S) > (size_t)prop.sharedMemPerBlockOptin)
-            throw CudaError{"RANGE: max_family_size too large for the shared-memory resident child vector"};
+        if (PruneCfg<13, 1>::smem_bytes(c->S) + 64 * 1024 > (size_t)prop.sharedMemPerBlockOptin)
+            throw CudaError{"RANGE: max_family_size too large for the shared-memory resident vector of the Pupko kernel"};
 
         // ---- families: validate, build the reference list (identical count vectors pruned once) ----
         c->F = n_families;
@@ -730,6 +793,43 @@ int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matri
 }
 
 int64_t cafe_b200_unique_families(const cafe_b200_ctx* c) { return c ? c->U : 0; }
+
+int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops)
+{
+    try {
+        if (!tflops) throw CudaError{"ARG: null output"};
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        double* d = nullptr;
+        CK(cudaMalloc(&d, 64));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+        double best = 0.0;
+        for (int rep = 0; rep < 6; ++rep) {
+            CK(cudaEventRecord(e0));
+            if (use_dmma) dmma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            else dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            // DFMA: 16 fma per thread-iteration; DMMA: 8 tiles x (8*8*4) fma per warp-iteration
+            double fma_count = use_dmma ? (double)blocks * (threads / 32) * iters * 8.0 * 256.0
+                                        : (double)blocks * threads * iters * 16.0;
+            double tf = 2.0 * fma_count / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(d);
+        *tflops = best;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(nullptr, e); }
+}
 int32_t cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->N : 0; }
 
 int cafe_b200_get_matrix(cafe_b200_ctx* c, double lambda, double branch_length, double* out)
@@ -772,7 +872,7 @@ int cafe_b200_root_vectors(cafe_b200_ctx* c, const double* lambdas, int32_t n_la
         PruneParams p = base_params(c, 1, MODE_ROOTS);
         c->d_roots.reserve((size_t)c->U * c->R);
         p.out_roots = c->d_roots.p;
-        launch_prune(c, p);
+        if (c->use_dmma) launch_dmma(c, p); else launch_prune(c, p);
         std::vector<double> roots((size_t)c->U * c->R);
         CK(cudaMemcpyAsync(roots.data(), c->d_roots.p, roots.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));

@@ -1,0 +1,239 @@
+// prune_dmma.cuh -- pruning kernel, FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) variant.
+//
+// Same algorithm, schedule, scratch-slot protocol and fused root epilogue as prune_kernel (kernels.cuh);
+// what changes is the contraction P(BM x S) . V(S x BN) of every internal branch:
+//   * accumulators are 8x8 DMMA tiles (2 doubles per thread per tile) instead of per-thread DFMA tiles, so one
+//     A fragment load feeds 8 columns and one B fragment load feeds 8 rows: 4x fewer shared-memory wavefronts
+//     per FMA than the DFMA kernel, whose LSU pipe was the co-limiter (profiles/r01_prune_dfma_ncu.txt);
+//   * BOTH operands are streamed through one cp.async pipeline (A = 16 rows of the transposed matrix, B = 16 rows
+//     of the child's vector tile), so no child vector stays resident in shared memory and the column tile can be
+//     128 wide (half the matrix traffic per FMA).
+// 8 warps as 2 (rows) x 4 (columns); warp tile = (8*TMW) x (8*TNW); CTA tile BM = 16*TMW rows x BN = 32*TNW columns.
+#pragma once
+#include "kernels.cuh"
+
+namespace cafe {
+
+constexpr int DM_BK = 16;
+
+template <int TMW, int TNW>
+struct DmmaCfg {
+    static constexpr int BM = 16 * TMW;
+    static constexpr int BN = 32 * TNW;
+    static constexpr int BMP = BM + 4;   // row strides = 32 bytes mod 128: fragment loads are bank-conflict free
+    static constexpr int BNP = BN + 4;
+    static constexpr int STAGE_DOUBLES = DM_BK * (BMP + BNP);
+    static int stages(size_t smem_limit)
+    {
+        int s = (int)(smem_limit / (sizeof(double) * STAGE_DOUBLES));
+        return s > 4 ? 4 : s;
+    }
+    static size_t smem_bytes(int n_stages) { return sizeof(double) * (size_t)n_stages * STAGE_DOUBLES; }
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int TMW, int TNW>
+__global__ void __launch_bounds__(PRUNE_THREADS, 1)
+prune_dmma_kernel(const PruneParams p, const int n_stages)
+{
+    using Cfg = DmmaCfg<TMW, TNW>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, BK = DM_BK;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
+    const int g = lane >> 2, q = lane & 3;            // DMMA fragment coordinates
+    const int row_base = wm * 8 * TMW + g;            // + i*8
+    const int col_base = wn * 8 * TNW + 2 * q;        // + j*8 + e
+    const int n_tiles = p.K * p.n_col_tiles;
+    double* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * p.slot_stride;
+    const int kpad = (p.S + BK - 1) / BK * BK;
+    const int n_chunks = kpad / BK;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int k = tile / p.n_col_tiles;
+        const int64_t col0 = (int64_t)(tile % p.n_col_tiles) * BN;
+        const int32_t* mat_of = p.mat_of + (size_t)k * p.n_nodes;
+
+        for (int st = 0; st < p.n_steps; ++st) {
+            const Step sp = p.steps[st];
+            double* const out_slot = my_scratch + (size_t)sp.out_slot * p.slot_stride;
+            for (int mt = 0; mt < p.n_mtiles; ++mt) {
+                const int m0 = mt * BM;
+                double acc[TMW][TNW][2];
+                bool has_acc = false;
+                for (int ci = 0; ci < sp.n_children; ++ci) {
+                    const StepChild ch = p.children[sp.child_begin + ci];
+                    const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
+                    if (ch.leaf_row >= 0) {
+                        // ---- leaf child: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
+#pragma unroll
+                        for (int j = 0; j < TNW; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                int64_t u = col0 + col_base + j * 8 + e;
+                                if (u >= p.U) u = p.U - 1;     // padding columns replay the last family; never written out
+                                const int obs = p.counts_t[(size_t)ch.leaf_row * p.U_stride + u];
+                                if (p.em == nullptr) {
+                                    const double* __restrict__ r = PT + (size_t)obs * p.LD + m0 + row_base;
+#pragma unroll
+                                    for (int i = 0; i < TMW; ++i) {
+                                        const double v = __ldg(r + i * 8);
+                                        acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], v) : v;
+                                    }
+                                } else {
+                                    const int er = obs < p.em_rows ? obs : p.em_rows - 1;
+                                    double pe[3];
+                                    const double* r[3];
+#pragma unroll
+                                    for (int d = 0; d < 3; ++d) {
+                                        const int idx = obs - 1 + d;
+                                        const bool ok = idx >= 0 && idx < p.S;
+                                        pe[d] = ok ? __ldg(p.em + er * 3 + d) : 0.0;
+                                        r[d] = PT + (size_t)(ok ? idx : obs) * p.LD + m0 + row_base;
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < TMW; ++i) {
+                                        double f = __dmul_rn(__ldg(r[0] + i * 8), pe[0]);       // c ascending, separately rounded
+                                        f = __dadd_rn(f, __dmul_rn(__ldg(r[1] + i * 8), pe[1]));
+                                        f = __dadd_rn(f, __dmul_rn(__ldg(r[2] + i * 8), pe[2]));
+                                        acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], f) : f;
+                                    }
+                                }
+                            }
+                    } else {
+                        // ---- internal child: acc = P[m0.., 0..S) . V_child   (matrix_cache.cpp:49-56)
+                        if (has_acc) {   // park the running product in the output slot while the tiles accumulate
+#pragma unroll
+                            for (int i = 0; i < TMW; ++i)
+#pragma unroll
+                                for (int j = 0; j < TNW; ++j)
+                                    *reinterpret_cast<double2*>(out_slot + (size_t)(m0 + row_base + i * 8) * BN + col_base + j * 8) =
+                                        make_double2(acc[i][j][0], acc[i][j][1]);
+                        }
+                        __syncthreads();   // every warp is done with the previous contraction's stages
+                        const double* __restrict__ src = my_scratch + (size_t)ch.slot * p.slot_stride;
+                        auto load_chunk = [&](int chunk) {
+                            if (chunk < n_chunks) {
+                                double* As = smem + (size_t)(chunk % n_stages) * Cfg::STAGE_DOUBLES;
+                                double* Bs = As + BK * BMP;
+                                const int k0 = chunk * BK;
+                                const double* __restrict__ ga = PT + (size_t)k0 * p.LD + m0;
+                                for (int idx = tid; idx < BK * (BM / 2); idx += PRUNE_THREADS) {
+                                    const int kk = idx / (BM / 2), mm = (idx % (BM / 2)) * 2;
+                                    cp_async16(As + kk * BMP + mm, ga + (size_t)kk * p.LD + mm);
+                                }
+                                for (int idx = tid; idx < BK * (BN / 2); idx += PRUNE_THREADS) {
+                                    const int kk = idx / (BN / 2), nn = (idx % (BN / 2)) * 2;
+                                    if (k0 + kk < p.S) cp_async16(Bs + kk * BNP + nn, src + (size_t)(k0 + kk) * BN + nn);
+                                    else { Bs[kk * BNP + nn] = 0.0; Bs[kk * BNP + nn + 1] = 0.0; }   // states >= S do not exist
+                                }
+                            }
+                            cp_async_commit();
+                        };
+                        for (int s = 0; s < n_stages - 1; ++s) load_chunk(s);
+#pragma unroll
+                        for (int i = 0; i < TMW; ++i)
+#pragma unroll
+                            for (int j = 0; j < TNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+                        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                            if (n_stages == 4) cp_async_wait<2>();
+                            else if (n_stages == 3) cp_async_wait<1>();
+                            else cp_async_wait<0>();
+                            __syncthreads();
+                            load_chunk(chunk + n_stages - 1);
+                            const double* As = smem + (size_t)(chunk % n_stages) * Cfg::STAGE_DOUBLES;
+                            const double* Bs = As + BK * BMP;
+#pragma unroll
+                            for (int k4 = 0; k4 < BK / 4; ++k4) {
+                                double a[TMW], b[TNW];
+                                const double* ap = As + (k4 * 4 + q) * BMP + row_base;
+                                const double* bp = Bs + (k4 * 4 + q) * BNP + wn * 8 * TNW + g;
+#pragma unroll
+                                for (int i = 0; i < TMW; ++i) a[i] = ap[i * 8];
+#pragma unroll
+                                for (int j = 0; j < TNW; ++j) b[j] = bp[j * 8];
+#pragma unroll
+                                for (int i = 0; i < TMW; ++i)
+#pragma unroll
+                                    for (int j = 0; j < TNW; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            }
+                        }
+                        cp_async_wait<0>();
+                        if (has_acc) {   // node_probs[i] *= result[i], children in descendant order (probability.cpp:215-217)
+#pragma unroll
+                            for (int i = 0; i < TMW; ++i)
+#pragma unroll
+                                for (int j = 0; j < TNW; ++j) {
+                                    const double2 prev = *reinterpret_cast<const double2*>(out_slot + (size_t)(m0 + row_base + i * 8) * BN + col_base + j * 8);
+                                    acc[i][j][0] = __dmul_rn(prev.x, acc[i][j][0]);
+                                    acc[i][j][1] = __dmul_rn(prev.y, acc[i][j][1]);
+                                }
+                        }
+                    }
+                    has_acc = true;
+                }
+#pragma unroll
+                for (int i = 0; i < TMW; ++i)
+#pragma unroll
+                    for (int j = 0; j < TNW; ++j)
+                        *reinterpret_cast<double2*>(out_slot + (size_t)(m0 + row_base + i * 8) * BN + col_base + j * 8) =
+                            make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+            if (sp.is_root) {
+                // ---- root epilogue: index j <-> root size j+1 (core.cpp:141), weighted by prior(j)
+                __syncthreads();
+                constexpr int PARTS = PRUNE_THREADS / BN;
+                const int c = tid % BN, part = tid / BN;
+                const int64_t u = col0 + c;
+                const double* root = out_slot + c;
+                double* red = smem;             // [PARTS][BN] best, then [PARTS][BN] any
+                double best;
+                int any = 0;
+                if (p.mode == MODE_BASE) {
+                    best = -INFINITY;           // max_j log L_j + log prior_j   (base_model.cpp:82-91)
+                    for (int j = part; j < p.R; j += PARTS) {
+                        const double v = __dadd_rn(log(root[(size_t)(j + 1) * BN]), p.logprior[j]);
+                        if (v > best) best = v;
+                    }
+                } else if (p.mode == MODE_GAMMA) {
+                    best = 0.0;                 // max_j L_j * prior_j ; failure iff sum_j L_j == 0   (gamma_core.cpp:151-160)
+                    bool first = true;
+                    for (int j = part; j < p.R; j += PARTS) {
+                        const double L = root[(size_t)(j + 1) * BN];
+                        any |= (L != 0.0);
+                        const double v = __dmul_rn(L, p.prior_d[j]);
+                        if (first || v > best) { best = v; first = false; }
+                    }
+                } else {
+                    best = 0.0;
+                    if (u < p.U && k == 0)
+                        for (int j = part; j < p.R; j += PARTS) p.out_roots[(size_t)u * p.R + j] = root[(size_t)(j + 1) * BN];
+                }
+                red[part * BN + c] = best;
+                red[(PARTS + part) * BN + c] = (double)any;
+                __syncthreads();
+                if (part == 0 && u < p.U && p.mode != MODE_ROOTS) {
+                    double bb = red[c];
+                    int aa = red[PARTS * BN + c] != 0.0;
+                    for (int qq = 1; qq < PARTS; ++qq) {
+                        const double v = red[qq * BN + c];
+                        if (v > bb) bb = v;
+                        aa |= red[(PARTS + qq) * BN + c] != 0.0;
+                    }
+                    p.out_best[(size_t)k * p.U_stride + u] = bb;
+                    if (p.mode == MODE_GAMMA) p.out_ok[(size_t)k * p.U_stride + u] = (uint8_t)aa;
+                }
+            }
+            __syncthreads();   // the slot just written is read by a later step
+        }
+    }
+}
+
+}  // namespace cafe

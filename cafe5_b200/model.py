@@ -211,6 +211,16 @@ class Context:
         return dict(launches=nl.value, matrices=nm.value, ms_matrices=a.value, ms_prune=b.value)
 
 
+def measure_fp64_peak(device=0, use_dmma=False):
+    """TFLOP/s of the FP64 pipe on `device` (DFMA chains or DMMA tiles), measured by a microbenchmark kernel."""
+    lib = _lib.load()
+    out = C.c_double()
+    rc = lib.cafe_b200_measure_fp64_peak(int(device), 1 if use_dmma else 0, C.byref(out))
+    if rc:
+        raise CafeError("measure_fp64_peak: %s" % lib.cafe_b200_last_error(None).decode())
+    return out.value
+
+
 class model:
     """Common part of base_model / gamma_model (reference src/core.h:125-189)."""
 

@@ -92,6 +92,8 @@ class FlatTree:
     reverse level order."""
 
     def __init__(self, newick, lambda_newick=None, species=None):
+        self.newick = newick
+        self.lambda_newick = lambda_newick
         root = parse_newick(newick)
         order = list(reversed(bfs(root)))
         index = {id(n): i for i, n in enumerate(order)}

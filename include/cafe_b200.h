@@ -132,6 +132,10 @@ void* cafe_b200_stream(cafe_b200_ctx* ctx);
 int cafe_b200_last_stats(cafe_b200_ctx* ctx, int32_t* n_launches, int32_t* n_matrices,
                          float* ms_matrices, float* ms_prune);
 
+/* FP64 pipe microbenchmark on `device` (register-resident DFMA chains, or mma.sync m8n8k4 DMMA tiles when
+ * use_dmma != 0): the roofline denominator of the pruning kernel, measured on the GPU the bench runs on. */
+int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops);
+
 /* Number of distinct count vectors actually pruned (the reference list's unique entries). */
 int64_t cafe_b200_unique_families(const cafe_b200_ctx* ctx);
 

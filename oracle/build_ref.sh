@@ -35,7 +35,7 @@ cat > "$OUT/config.h" <<'CFG'
 #define MATRIX 6
 #define INFERENCE 8
 CFG
-FLAGS=(-std=c++11 -O2 -fopenmp -fPIC -w -fno-access-control -include "$OUT/config.h" -I"$REF/src"
+FLAGS=(-std=c++11 -O2 -fopenmp -fPIC -w -fno-access-control -include "$OUT/config.h" -I"$REF/src" -I"$HERE/../include"
        -DDOCTEST_CONFIG_DISABLE -DSILENT -DELPP_NO_CHECK_MACROS -DMODEL_GENE_EXPRESSION_LOGS
        -DOPTIMIZER_STRATEGY=NelderMead -DDISCRETIZATION_RANGE=200 -DMAX_STACK_FAMILY_SIZE=1000)
 objs=()
@@ -44,11 +44,19 @@ for src in "$REF"/src/*.cpp "$HERE/ref_driver.cpp" "$HERE/ref_gpu_model.cpp"; do
   [ -f "$src" ] || continue
   obj="$OUT/obj/$(basename "${src%.cpp}").o"
   objs+=("$obj")
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../cafe5_b200/host/gpu_model.hpp" -nt "$obj" ]; then
     "$CXX" "${FLAGS[@]}" -c "$src" -o "$obj" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-"$CXX" -shared -fopenmp -o "$OUT/libcafe_ref.so" "${objs[@]}" -lz -ldl
+# the drop-in shim (ref_gpu_model.cpp) binds the product's C ABI: link libcafe_b200.so when it has been built
+LINK_GPU=()
+if [ -f "$HERE/../cafe5_b200/libcafe_b200.so" ]; then
+  LINK_GPU=(-L"$HERE/../cafe5_b200" -lcafe_b200 '-Wl,-rpath,$ORIGIN/../../cafe5_b200')
+else
+  echo "libcafe_b200.so not built yet: build it first (python -c 'import __graft_entry__ as g; g.build()')" >&2
+  exit 1
+fi
+"$CXX" -shared -fopenmp -o "$OUT/libcafe_ref.so" "${objs[@]}" "${LINK_GPU[@]}" -lz -ldl
 echo "built $OUT/libcafe_ref.so"

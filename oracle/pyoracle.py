@@ -247,6 +247,16 @@ class RefLib:
         L.ref_reconstruct_gamma.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip, c_dp]
         L.ref_set_threads.argtypes = [C.c_int]
         L.ref_max_threads.restype = C.c_int
+        L.ref_optimize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, c_dp, c_ip, c_dp, c_ip, c_ip, c_dp]
+        L.ref_ctx_error.restype = C.c_char_p
+        L.ref_ctx_error.argtypes = [C.c_void_p]
+        L.ref_time_precalculate.restype = C.c_double
+        L.ref_time_precalculate.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_int, C.c_int, c_ip, c_ip]
+        L.ref_session_create.restype = C.c_void_p
+        L.ref_session_create.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int]
+        L.ref_session_destroy.argtypes = [C.c_void_p]
+        L.ref_session_prune.restype = C.c_double
+        L.ref_session_prune.argtypes = [C.c_void_p, C.c_void_p, C.c_long, c_dp]
 
     def _check(self, rc):
         if rc:
@@ -350,6 +360,17 @@ class RefLib:
                                                         C.byref(neg), _dp(cat), _up(failed)))
             return dict(neg_lnl=neg.value, cat_lk=cat, failed=failed)
 
+        def optimize(self, backend, n_cat=0, optimize_epsilon=False, seed=10, device=0):
+            """Run the reference's optimizer (Nelder-Mead) with backend 'cpu' (reference models) or 'gpu' (CUDA shim)."""
+            vals = np.zeros(16)
+            nv, iters, attempts = C.c_int(), C.c_int(), C.c_int()
+            score, secs = C.c_double(), C.c_double()
+            rc = self.ref.lib.ref_optimize(self.h, 1 if backend == "gpu" else 0, int(n_cat), 1 if optimize_epsilon else 0, int(seed),
+                                           int(device), _dp(vals), C.byref(nv), C.byref(score), C.byref(iters), C.byref(attempts), C.byref(secs))
+            if rc:
+                raise RuntimeError("ref_optimize: " + self.ref.lib.ref_ctx_error(self.h).decode())
+            return dict(values=vals[:nv.value].copy(), score=score.value, iterations=iters.value, attempts=attempts.value, seconds=secs.value)
+
         def reconstruct_base(self, lambdas):
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
             st = np.zeros((self.F, self.n_nodes), dtype=np.int32)
@@ -370,3 +391,32 @@ class RefLib:
 
     def ctx(self, *a, **k):
         return RefLib.Ctx(self, *a, **k)
+
+    # timing legs for bench.py (see oracle/ref_driver.cpp)
+    def time_precalculate(self, ctx, lambdas, multipliers, stride):
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        mu = np.ascontiguousarray(multipliers, dtype=np.float64)
+        done, total = C.c_int(), C.c_int()
+        t = self.lib.ref_time_precalculate(ctx.h, _dp(lam), len(lam), _dp(mu), len(mu), int(stride), C.byref(done), C.byref(total))
+        if t < 0:
+            self._check(1)
+        return t, done.value, total.value
+
+    def session(self, ctx, lambdas, multipliers, cat_probs):
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        mu = np.ascontiguousarray(multipliers, dtype=np.float64)
+        cp = np.ascontiguousarray(cat_probs, dtype=np.float64)
+        h = self.lib.ref_session_create(ctx.h, _dp(lam), len(lam), _dp(mu), _dp(cp), len(mu))
+        if not h:
+            self._check(1)
+        return h
+
+    def session_prune(self, ctx, session, n):
+        out = C.c_double()
+        t = self.lib.ref_session_prune(ctx.h, session, int(n), C.byref(out))
+        if t < 0:
+            self._check(1)
+        return t, out.value
+
+    def session_destroy(self, session):
+        self.lib.ref_session_destroy(session)

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <numeric>
 #include <random>
 #include <sstream>
 #include <string>
@@ -355,6 +356,88 @@ int ref_reconstruct_gamma(void* h, const double* lambdas, int n_lambda, const do
         }
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// ---- timing helpers for bench.py (cpu_baseline / --impl reference) ---------------------------------
+// A full reference evaluation on the config-5 shard takes minutes (about 400 matrices at ~0.1 s each plus
+// ~50 ms per family per thread), so the bench times BOUNDED SAMPLES of its two legs, each through the
+// reference's own functions, and scales them linearly (documented in bench.py / DESIGN.md):
+//   leg 1: matrix_cache::precalculate_matrices on every `stride`-th branch length  (src/matrix_cache.cpp:113-163)
+//   leg 2: gamma_model::prune (+ the mixture of gamma_core.cpp:196-207) over the first n families under the
+//          reference's `#pragma omp parallel for` shape (gamma_core.cpp:190), against a prebuilt full cache.
+struct ref_session {
+    std::unique_ptr<lambda> lam;
+    std::unique_ptr<gamma_model> model;
+    std::unique_ptr<matrix_cache> cache;
+    int K = 0;
+};
+
+double ref_time_precalculate(void* h, const double* lambdas, int n_lambda, const double* multipliers, int K,
+                             int stride, int* keys_done, int* keys_total)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::vector<double> all;
+        for (int k = 0; k < K; ++k) for (int i = 0; i < n_lambda; ++i) all.push_back(lambdas[i] * multipliers[k]);
+        auto bls = c->tree->get_branch_lengths();
+        std::set<double> sample;
+        int idx = 0;
+        for (double b : bls) if ((idx++ % stride) == 0) sample.insert(b);
+        matrix_cache cache(std::max(c->max_root_family_size, c->max_family_size) + 1);
+        double t0 = omp_get_wtime();
+        cache.precalculate_matrices(all, sample);
+        double t1 = omp_get_wtime();
+        if (keys_done) *keys_done = cache.get_cache_size();
+        if (keys_total) *keys_total = int(all.size() * bls.size());
+        return t1 - t0;
+    } catch (std::exception& e) { g_err = e.what(); return -1.0; }
+}
+
+void* ref_session_create(void* h, const double* lambdas, int n_lambda, const double* multipliers, const double* cat_probs, int K)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        auto s = new ref_session();
+        s->K = K;
+        s->lam.reset(make_lambda(c, lambdas, n_lambda));
+        std::vector<gene_family> none;
+        s->model.reset(new gamma_model(s->lam.get(), c->tree.get(), nullptr, c->max_family_size, c->max_root_family_size,
+                                       std::vector<double>(cat_probs, cat_probs + K), std::vector<double>(multipliers, multipliers + K), c->em.get()));
+        s->model->_alpha = 1.0;
+        s->cache.reset(new matrix_cache(std::max(c->max_root_family_size, c->max_family_size) + 1));
+        s->model->prepare_matrices_for_simulation(*s->cache);   // the call infer_family_likelihoods makes (gamma_core.cpp:186)
+        return s;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+void ref_session_destroy(void* s) { delete (ref_session*)s; }
+
+// Seconds to prune + mix the first n families; sum_lnl gets the summed log-likelihood (0 families failed) or NaN.
+double ref_session_prune(void* h, void* sh, long n, double* sum_lnl)
+{
+    auto c = (ref_ctx*)h;
+    auto s = (ref_session*)sh;
+    try {
+        std::vector<double> lnl(n, 0.0);
+        std::vector<char> bad(n, 0);
+        double t0 = omp_get_wtime();
+#pragma omp parallel for
+        for (long i = 0; i < n; ++i) {
+            std::vector<double> cat;
+            if (s->model->prune(c->ud.gene_families[i], c->ud.prior, *s->cache, s->lam.get(), cat)) {
+                double fam = std::accumulate(cat.begin(), cat.end(), 0.0);
+                auto post = s->model->get_posterior_probabilities(cat);
+                (void)post;
+                lnl[i] = std::log(fam);
+            } else bad[i] = 1;
+        }
+        double t1 = omp_get_wtime();
+        double tot = 0;
+        bool any_bad = false;
+        for (long i = 0; i < n; ++i) { tot += lnl[i]; any_bad |= bad[i] != 0; }
+        if (sum_lnl) *sum_lnl = any_bad ? std::nan("") : tot;
+        return t1 - t0;
+    } catch (std::exception& e) { g_err = e.what(); return -1.0; }
 }
 
 // Viterbi branch p-value (src/gene_family_reconstructor.cpp:390-429) restated through the matrix only:

@@ -1,0 +1,151 @@
+"""Host-side logic that needs no GPU: tree flattening, family tables, derived sizes, gamma discretisation,
+sharding, and that the C-ABI library loads and exports every symbol include/cafe_b200.h declares."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cafe5_b200 import _lib, dist, families as fam
+from cafe5_b200.gamma import get_gamma
+from cafe5_b200.tree import FlatTree, parse_newick
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAMMALS = ("((((cat:68.710507,horse:68.710507):4.566782,cow:73.277289):20.722711,(((((chimp:4.444172,human:4.444172):6.682678,"
+           "orang:11.126850):2.285855,gibbon:13.412706):7.211527,(macaque:4.567240,baboon:4.567240):16.056992):16.060702,"
+           "marmoset:36.684935):57.315065):38.738021,(rat:36.302445,mouse:36.302445):96.435575);")
+
+
+def test_reverse_level_order_and_names():
+    t = FlatTree("((A:1,B:3):7,(C:11,D:17):23)")
+    assert t.names == ["D", "C", "B", "A", "CD", "AB", "ABCD"]        # reference clade.cpp:69-100, :161-173
+    assert list(t.parent) == [4, 4, 5, 5, 6, 6, -1]
+    assert list(t.branch_length) == [17, 11, 3, 1, 23, 7, 0]
+    assert t.children_of(6) == [5, 4] and t.children_of(5) == [3, 2]  # descendant order = decreasing index
+
+
+def test_flatten_matches_reference(ref, golden):
+    for nw, lnw in [(MAMMALS, None), (str(golden["mammals"]["newick"]), str(golden["mammals"]["lambda_newick"])),
+                    (str(golden["hymenoptera"]["newick"]), None), ("((A:2.5,B:2.5,C:2.5):4,(D:3,(E:1,F:1):2):3.5)", None)]:
+        t = FlatTree(nw, lnw)
+        parent, bl, is_leaf, lc, names = ref.flatten(nw, lnw)
+        assert t.names == names
+        assert np.array_equal(t.parent, parent) and np.array_equal(t.branch_length, bl)
+        assert np.array_equal(t.is_leaf, is_leaf.astype(bool)) and np.array_equal(t.lambda_class, lc)
+
+
+def test_lambda_tree_classes(golden):
+    g = golden["mammals"]
+    t = FlatTree(str(g["newick"]), str(g["lambda_newick"]))
+    cls = dict(zip(t.names, t.lambda_class))
+    assert cls["chimp"] == cls["human"] == cls["chimphuman"] == 1 and cls["orang"] == 0 and t.n_lambda == 2
+    with pytest.raises(ValueError):
+        FlatTree("((A:1,B:1):1,C:2)", "((A:1,X:1):1,C:1)")
+    with pytest.raises(ValueError):
+        parse_newick("(A:1,B:0)")       # clade.cpp:411-414: non-root branch lengths must be > 0
+
+
+def test_interior_labels_are_kept(golden):
+    t = FlatTree(str(golden["hymenoptera"]["newick"]))
+    assert t.n_leaves == 10 and t.n_nodes == 19
+
+
+def test_family_table_formats(tmp_path):
+    p = tmp_path / "cafe.txt"
+    p.write_text("Desc\tFamily ID\tA\tB\n\t f1\t5\t10\n\n\t f2\t5\t7\n")
+    species, ids, counts = fam.read_gene_families(str(p))
+    assert species == ["A", "B"] and ids == [" f1", " f2"] and counts.tolist() == [[5, 10], [5, 7]]
+    p2 = tmp_path / "cafexp.txt"
+    p2.write_text("#A\n#B\n3\t4\tfamX\n1\t0\tfamY\n")
+    species, ids, counts = fam.read_gene_families(str(p2))
+    assert species == ["A", "B"] and ids == ["famX", "famY"] and counts.tolist() == [[3, 4], [1, 0]]
+    p3 = tmp_path / "empty.txt"
+    p3.write_text("Desc\tFamily ID\tA\tB\n")
+    with pytest.raises(ValueError):
+        fam.read_gene_families(str(p3))
+
+
+def test_derived_sizes():
+    # reference user_data.h:26-27 floors and user_data.cpp:40-48
+    assert fam.derive_sizes(np.array([[3, 72]])) == (170, 150)
+    assert fam.derive_sizes(np.array([[150, 2]])) == (200, 188)
+    assert fam.derive_sizes(np.array([[200, 2]])) == (250, 250)
+
+
+def test_root_filter(golden):
+    t = FlatTree("((A:1,B:3):7,(C:11,D:17):23)")
+    counts = np.array([[1, 0, 0, 0], [1, 0, 0, 2], [0, 0, 3, 3], [0, 1, 1, 0]])   # columns D, C, B, A
+    assert fam.exists_at_root(t, counts).tolist() == [False, True, False, True]
+    g = golden["mammals"]
+    assert int(g["n_before_filter"]) == 12653 and g["counts"].shape[0] == 10956   # SURVEY 3.1 [measured]
+
+
+def test_uniform_prior_is_float():
+    p = fam.uniform_prior(150)
+    assert p.dtype == np.float32 and float(np.float64(p[0])) == 0.0066666668280959129
+    r = fam.rootdist_prior({1: 2, 2: 2, 3: 2, 4: 2, 5: 1})
+    assert r[0] == 0 and r[5] == np.float32(1) / np.float32(9)
+
+
+def test_error_model_file_and_epsilon_table(tmp_path):
+    p = tmp_path / "em.txt"
+    p.write_text("maxcnt: 20\ncntdiff -1 0 1\n0 0.0 0.8 0.2\n1 0.2 0.6 0.2\n20 0.2 0.6 0.2\n")
+    probs, maxcnt = fam.read_error_model(str(p))
+    assert maxcnt == 20 and probs.shape == (21, 3) and probs[7].tolist() == [0.2, 0.6, 0.2]
+    rows, _ = fam.epsilon_error_model(0.05, 10)
+    assert rows[0].tolist() == [0.0, 0.95, 0.05] and rows[3].tolist() == [0.05, 1 - 0.1, 0.05]
+    from cafe5_b200.model import error_model
+    em = error_model(rows, 10)
+    em.update_single_epsilon(0.07)                       # error_model.cpp:70-109
+    assert em.probs[0].tolist() == [0.0, 1 - 0.07, 0.07] and em.probs[5].tolist() == [0.07, 1 - 0.14, 0.07]
+
+
+def test_get_gamma_matches_reference(ref):
+    for K in (2, 3, 4, 8):
+        for alpha in (0.05, 0.3, 0.6, 0.65, 0.7, 1.0, 1.7, 5.0, 40.0):
+            p, m = get_gamma(K, alpha)
+            pr, mr = ref.get_gamma(K, alpha)
+            assert np.array_equal(m, mr) and np.array_equal(p, pr)
+
+
+def test_get_gamma_known_answer():
+    assert get_gamma(4, 0.65)[1] == [0.062015465425384449, 0.37328920830134099, 0.99805780528212318, 2.5666375209911516]
+
+
+def test_shard_bounds_cover_everything():
+    for F in (1, 7, 10956, 1000000):
+        for W in (1, 2, 3, 8):
+            spans = [dist.shard_bounds(F, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == F
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_combine_partials_rejects_failures():
+    assert dist.combine_partials([(1.5, 0), (2.25, 0)]) == (3.75, 0)
+    assert dist.combine_partials([(1.5, 0), (math.inf, 0)])[0] == math.inf
+    assert dist.combine_partials([(1.5, 2), (2.0, 0)]) == (math.inf, 2)
+
+
+def test_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cafe_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cafe_b200_[a-z_]+)\s*\(", header)))
+    assert declared == sorted(_lib.SYMBOLS)
+    assert os.path.exists(_lib.LIB_PATH), "libcafe_b200.so must be built in-tree (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_create_fails_loudly_without_a_gpu():
+    """There is no CPU fallback: without a CUDA device create must return an error, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from cafe5_b200.model import CafeError, Context
+    t = FlatTree("(A:1,B:1);")
+    with pytest.raises(CafeError):
+        Context(t, np.array([[1, 2]], dtype=np.int32), 56, 8)

@@ -1,0 +1,74 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU plumbing: contiguous family shards, one 16-byte exchange per
+step, partials combined in fixed rank order.  The per-shard evaluator here is the C oracle (tests may use it);
+on GPUs the same helpers wrap the CUDA context (bench.py)."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from cafe5_b200 import dist as cdist
+from cafe5_b200 import families as fam
+from cafe5_b200.tree import FlatTree
+
+NEWICK = "((A:1,B:3):7,(C:11,D:17):23)"
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _counts():
+    rng = np.random.default_rng(123)
+    return rng.integers(1, 25, size=(41, 4)).astype(np.int32)
+
+
+def _worker(rank, world, port, fail, out_queue):
+    import torch.distributed as dist
+    from oracle.pyoracle import OracleLib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = OracleLib()
+    o.set_threads(1)
+    tree = FlatTree(NEWICK)
+    counts = _counts()
+    lo, hi = cdist.shard_bounds(counts.shape[0], world, rank)
+    prior = fam.uniform_prior(45)
+    if fail:   # a saturated category kills every family of every shard -> +inf everywhere
+        r = o.eval_gamma(tree, counts[lo:hi], 60, 45, prior, [0.04], [0.1, 2.0], [0.5, 0.5])
+    else:
+        r = o.eval_gamma(tree, counts[lo:hi], 60, 45, prior, [0.01], [0.5, 1.5], [0.5, 0.5])
+    total, nfail = cdist.allreduce_score(r["neg_lnl"], r["n_failed"])
+    out_queue.put((rank, total, nfail, lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail", [False, True])
+def test_two_rank_sharded_score(fail):
+    from oracle.pyoracle import OracleLib
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, fail, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][3:] == (0, 21) and results[1][3:] == (21, 41)
+    assert results[0][1:3] == results[1][1:3]            # every rank ends with the identical score
+    o = OracleLib()
+    tree = FlatTree(NEWICK)
+    prior = fam.uniform_prior(45)
+    if fail:
+        assert results[0][1] == math.inf and results[0][2] > 0
+    else:
+        whole = o.eval_gamma(tree, _counts(), 60, 45, prior, [0.01], [0.5, 1.5], [0.5, 0.5])
+        assert abs(results[0][1] - whole["neg_lnl"]) <= 1e-13 * whole["neg_lnl"] and results[0][2] == 0
