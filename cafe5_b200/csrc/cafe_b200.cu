@@ -107,7 +107,7 @@ struct cafe_b200_ctx {
     DevBuf<int64_t> d_f2u;
     DevBuf<Step> d_steps;
     DevBuf<StepChild> d_children;
-    DevBuf<double> d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
+    DevBuf<double> d_zero, d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
     DevBuf<uint8_t> d_ok;
     DevBuf<MatParam> d_params;
     DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
@@ -191,7 +191,13 @@ void build_schedule(cafe_b200_ctx* c)
         else s = n_slots++;
         st.out_slot = s;
         slot_of[v] = s;
-        for (int k : kids[v]) {
+        std::vector<int> order_kids = kids[v];
+        // A two-child product is commutative bit for bit, so the contraction (internal child) goes first and the
+        // leaf factor is multiplied into the accumulators in registers: no parking of the running product.
+        // Three or more children keep the reference's descendant order (the association matters there).
+        if (order_kids.size() == 2 && c->leaf_col[order_kids[0]] >= 0 && c->leaf_col[order_kids[1]] < 0)
+            std::swap(order_kids[0], order_kids[1]);
+        for (int k : order_kids) {
             StepChild ch{};
             ch.node = k;
             ch.leaf_row = c->leaf_col[k] >= 0 ? c->leaf_row_of_node[k] : -1;
@@ -295,10 +301,12 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
         if (tiles >= 2 * (int64_t)c->n_sms) break;
         tnw >>= 1;
     }
+    if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);   // experiment knob
     c->TNW = tnw;
     const int bn = 32 * tnw, bm = 16 * c->TM;
     const size_t stage = sizeof(double) * (size_t)DM_BK * (bm + 4 + bn + 4);
-    int stages = (int)(c->smem_optin / stage);
+    const size_t tail = sizeof(double) * (2 * PRUNE_THREADS + 8);
+    int stages = (int)((c->smem_optin - tail) / stage);
     c->dmma_stages = stages > 4 ? 4 : stages;
     if (c->dmma_stages < 2) throw CudaError{"RANGE: state space too large for the pruning pipeline"};
     c->n_col_tiles = (int)((c->U + bn - 1) / bn);
@@ -406,6 +414,7 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     p.out_best = c->d_best.p;
     p.out_ok = c->d_ok.p;
     p.out_roots = nullptr;
+    p.zero_row = c->d_zero.p;
     p.U = c->U;
     p.U_stride = c->U_stride;
     p.n_steps = (int)c->steps.size();
@@ -612,6 +621,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->d_f2u.reserve(n_families);
         CK(cudaMemcpy(c->d_f2u.p, c->f2u.data(), (size_t)n_families * sizeof(int64_t), cudaMemcpyHostToDevice));
 
+        c->d_zero.reserve(256, true);
         build_schedule(c);
         c->d_steps.reserve(c->steps.size());
         CK(cudaMemcpy(c->d_steps.p, c->steps.data(), c->steps.size() * sizeof(Step), cudaMemcpyHostToDevice));
@@ -643,7 +653,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_counts_t.release(); c->d_mat_of.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
-    c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
+    c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
     c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
     c->d_partial.release(); c->d_partial_fail.release(); c->d_result.release(); c->d_roots.release();

@@ -5,9 +5,11 @@
 //   * accumulators are 8x8 DMMA tiles (2 doubles per thread per tile) instead of per-thread DFMA tiles, so one
 //     A fragment load feeds 8 columns and one B fragment load feeds 8 rows: 4x fewer shared-memory wavefronts
 //     per FMA than the DFMA kernel, whose LSU pipe was the co-limiter (profiles/r01_prune_dfma_ncu.txt);
-//   * BOTH operands are streamed through one cp.async pipeline (A = 16 rows of the transposed matrix, B = 16 rows
-//     of the child's vector tile), so no child vector stays resident in shared memory and the column tile can be
-//     128 wide (half the matrix traffic per FMA).
+//   * BOTH operands are streamed through one bulk-async-copy pipeline (cp.async.bulk + mbarrier full/empty pairs:
+//     A = 16 rows of the transposed matrix, B = 16 rows of the child's vector tile, one 1-1.4 KB row copy per lane of
+//     warp 0), so no child vector stays resident in shared memory, the column tile can be 128 wide (half the matrix
+//     traffic per FMA), no thread spends issue slots on address arithmetic and there is no CTA-wide barrier inside
+//     the contraction.
 // 8 warps as 2 (rows) x 4 (columns); warp tile = (8*TMW) x (8*TNW); CTA tile BM = 16*TMW rows x BN = 32*TNW columns.
 #pragma once
 #include "kernels.cuh"
@@ -23,13 +25,42 @@ struct DmmaCfg {
     static constexpr int BMP = BM + 4;   // row strides = 32 bytes mod 128: fragment loads are bank-conflict free
     static constexpr int BNP = BN + 4;
     static constexpr int STAGE_DOUBLES = DM_BK * (BMP + BNP);
-    static int stages(size_t smem_limit)
-    {
-        int s = (int)(smem_limit / (sizeof(double) * STAGE_DOUBLES));
-        return s > 4 ? 4 : s;
-    }
-    static size_t smem_bytes(int n_stages) { return sizeof(double) * (size_t)n_stages * STAGE_DOUBLES; }
+    static constexpr int MAX_STAGES = 4;
+    static constexpr int TAIL_DOUBLES = 2 * PRUNE_THREADS + 2 * MAX_STAGES;   // epilogue reduction + mbarriers
+    static size_t smem_bytes(int n_stages) { return sizeof(double) * ((size_t)n_stages * STAGE_DOUBLES + TAIL_DOUBLES); }
 };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one contiguous row, global -> shared, completion counted in bytes on an mbarrier (async proxy)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
 {
@@ -43,10 +74,21 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
 {
     using Cfg = DmmaCfg<TMW, TNW>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, BK = DM_BK;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem_dm[];
+    double* const smem = smem_dm;
+    double* const red = smem + (size_t)n_stages * Cfg::STAGE_DOUBLES;          // [2][PRUNE_THREADS] epilogue reduction
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(red + 2 * PRUNE_THREADS);
+    uint64_t* const empty_bar = full_bar + Cfg::MAX_STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, PRUNE_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    unsigned gc = 0;        // chunks consumed since kernel start (same in every thread): stage = gc % n_stages
+    unsigned gp = 0;        // chunks produced since kernel start (meaningful in warp 0)
     const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
     const int g = lane >> 2, q = lane & 3;            // DMMA fragment coordinates
     const int row_base = wm * 8 * TMW + g;            // + i*8
@@ -117,38 +159,38 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
                                     *reinterpret_cast<double2*>(out_slot + (size_t)(m0 + row_base + i * 8) * BN + col_base + j * 8) =
                                         make_double2(acc[i][j][0], acc[i][j][1]);
                         }
-                        __syncthreads();   // every warp is done with the previous contraction's stages
                         const double* __restrict__ src = my_scratch + (size_t)ch.slot * p.slot_stride;
-                        auto load_chunk = [&](int chunk) {
-                            if (chunk < n_chunks) {
-                                double* As = smem + (size_t)(chunk % n_stages) * Cfg::STAGE_DOUBLES;
-                                double* Bs = As + BK * BMP;
-                                const int k0 = chunk * BK;
-                                const double* __restrict__ ga = PT + (size_t)k0 * p.LD + m0;
-                                for (int idx = tid; idx < BK * (BM / 2); idx += PRUNE_THREADS) {
-                                    const int kk = idx / (BM / 2), mm = (idx % (BM / 2)) * 2;
-                                    cp_async16(As + kk * BMP + mm, ga + (size_t)kk * p.LD + mm);
-                                }
-                                for (int idx = tid; idx < BK * (BN / 2); idx += PRUNE_THREADS) {
-                                    const int kk = idx / (BN / 2), nn = (idx % (BN / 2)) * 2;
-                                    if (k0 + kk < p.S) cp_async16(Bs + kk * BNP + nn, src + (size_t)(k0 + kk) * BN + nn);
-                                    else { Bs[kk * BNP + nn] = 0.0; Bs[kk * BNP + nn + 1] = 0.0; }   // states >= S do not exist
-                                }
+                        // producer: lane l < 16 copies A row l of the chunk, lane 16 + l copies B row l
+                        auto produce = [&](int chunk) {
+                            const unsigned stage = gp % (unsigned)n_stages;
+                            mbar_wait(empty_bar + stage, ((gp / (unsigned)n_stages) & 1u) ^ 1u);   // all 8 warps released it
+                            double* As = smem + (size_t)stage * Cfg::STAGE_DOUBLES;
+                            double* Bs = As + BK * BMP;
+                            const int k0 = chunk * BK;
+                            if (lane == 0) mbar_expect_tx(full_bar + stage, (unsigned)(BK * (BM + BN) * sizeof(double)));
+                            __syncwarp();
+                            if (lane < BK) {
+                                bulk_g2s(As + lane * BMP, PT + (size_t)(k0 + lane) * p.LD + m0, BM * sizeof(double), full_bar + stage);
+                            } else {
+                                const int kk = lane - BK;
+                                // child states >= S do not exist: feed zeros (matrix rows there are real when N > S)
+                                const double* row = (k0 + kk < p.S) ? src + (size_t)(k0 + kk) * BN : p.zero_row;
+                                bulk_g2s(Bs + kk * BNP, row, BN * sizeof(double), full_bar + stage);
                             }
-                            cp_async_commit();
+                            ++gp;
                         };
-                        for (int s = 0; s < n_stages - 1; ++s) load_chunk(s);
+                        if (warp == 0) {
+                            asm volatile("fence.proxy.async;\n" ::: "memory");   // slot rows were written through the generic proxy
+                            for (int s = 0; s < n_stages - 1 && s < n_chunks; ++s) produce(s);
+                        }
 #pragma unroll
                         for (int i = 0; i < TMW; ++i)
 #pragma unroll
                             for (int j = 0; j < TNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
                         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                            if (n_stages == 4) cp_async_wait<2>();
-                            else if (n_stages == 3) cp_async_wait<1>();
-                            else cp_async_wait<0>();
-                            __syncthreads();
-                            load_chunk(chunk + n_stages - 1);
-                            const double* As = smem + (size_t)(chunk % n_stages) * Cfg::STAGE_DOUBLES;
+                            const unsigned stage = gc % (unsigned)n_stages;
+                            mbar_wait(full_bar + stage, (gc / (unsigned)n_stages) & 1u);
+                            const double* As = smem + (size_t)stage * Cfg::STAGE_DOUBLES;
                             const double* Bs = As + BK * BMP;
 #pragma unroll
                             for (int k4 = 0; k4 < BK / 4; ++k4) {
@@ -164,8 +206,11 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
 #pragma unroll
                                     for (int j = 0; j < TNW; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                             }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(empty_bar + stage);       // this warp is done reading the stage
+                            ++gc;
+                            if (warp == 0 && chunk + n_stages - 1 < n_chunks) produce(chunk + n_stages - 1);
                         }
-                        cp_async_wait<0>();
                         if (has_acc) {   // node_probs[i] *= result[i], children in descendant order (probability.cpp:215-217)
 #pragma unroll
                             for (int i = 0; i < TMW; ++i)
@@ -193,7 +238,6 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
                 const int c = tid % BN, part = tid / BN;
                 const int64_t u = col0 + c;
                 const double* root = out_slot + c;
-                double* red = smem;             // [PARTS][BN] best, then [PARTS][BN] any
                 double best;
                 int any = 0;
                 if (p.mode == MODE_BASE) {
