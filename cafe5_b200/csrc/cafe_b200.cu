@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "pupko.cuh"
 #include "prune_dmma.cuh"
+#include "prune_resident.cuh"
 #include "peak.cuh"
 
 #include <algorithm>
@@ -92,7 +93,12 @@ struct cafe_b200_ctx {
 
     // tiling choice
     int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
-    bool use_dmma = true;      // FP64 tensor-core contraction (default); CAFE_B200_PRUNE=dfma selects the DFMA kernel
+    // pruning kernel: 2 = DMMA with the child vector resident in shared memory (default when it fits),
+    // 1 = DMMA streaming both operands (large state spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=resident|stream|dfma
+    int prune_pref = 2, prune_kind = 2;
+    bool use_dmma = true;
+    std::vector<int32_t> gemm_nodes;
+    int n_fslots = 1;
     int TNW = 4, dmma_stages = 4;
     size_t smem_optin = 0;
 
@@ -103,7 +109,7 @@ struct cafe_b200_ctx {
     int em_rows = 0, em_maxcnt = 0;
 
     // device buffers
-    DevBuf<int32_t> d_counts_t, d_mat_of;
+    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;
     DevBuf<int64_t> d_f2u;
     DevBuf<Step> d_steps;
     DevBuf<StepChild> d_children;
@@ -211,6 +217,43 @@ void build_schedule(cafe_b200_ctx* c)
     for (size_t i = 0; i < c->steps.size(); ++i) step_of[c->steps[i].node] = (int)i;
     for (auto& st : c->steps) st.parent_step = c->parent[st.node] < 0 ? -1 : step_of[c->parent[st.node]];
     c->n_slots = n_slots;
+
+    // ---- resident kernel: which factor travels how ----
+    auto chain = [&](int v) {      // v's factor stays in registers: its parent is the very next step and has <= 2 children
+        if (c->leaf_col[v] >= 0 || c->parent[v] < 0) return false;
+        int P = c->parent[v];
+        return kids[P].size() <= 2 && step_of[P] == step_of[v] + 1;
+    };
+    std::vector<int> fslot_of(n, -1), free_f;
+    int n_f = 0;
+    c->gemm_nodes.clear();
+    for (auto& st : c->steps) {
+        const int v = st.node;
+        st.carry_in = 0;
+        for (int i = 0; i < st.n_children; ++i) {
+            StepChild& ch = c->children[st.child_begin + i];
+            if (c->leaf_col[ch.node] >= 0) { ch.kind = 0; ch.f_slot = -1; }
+            else if (chain(ch.node)) { ch.kind = 1; ch.f_slot = -1; st.carry_in = 1; }
+            else { ch.kind = 2; ch.f_slot = fslot_of[ch.node]; }
+        }
+        for (int i = 0; i < st.n_children; ++i) {      // slots of consumed factors are free again
+            const StepChild& ch = c->children[st.child_begin + i];
+            if (ch.kind == 2) free_f.push_back(ch.f_slot);
+        }
+        st.f_slot = -1;
+        if (st.is_root) st.dst_kind = 2;
+        else {
+            c->gemm_nodes.push_back(v);
+            if (chain(v)) st.dst_kind = 0;
+            else {
+                st.dst_kind = 1;
+                if (!free_f.empty()) { st.f_slot = free_f.back(); free_f.pop_back(); }
+                else st.f_slot = n_f++;
+                fslot_of[v] = st.f_slot;
+            }
+        }
+    }
+    c->n_fslots = std::max(n_f, 1);
 }
 
 void choose_tiling(cafe_b200_ctx* c)
@@ -292,6 +335,45 @@ void launch_dmma(cafe_b200_ctx* c, PruneParams& p)
     }
 }
 
+template <int TMW, int TNW>
+void launch_resident_t(cafe_b200_ctx* c, PruneParams& p)
+{
+    using Cfg = ResidentCfg<TMW, TNW>;
+    size_t smem = Cfg::smem_bytes(c->N);
+    CK(cudaFuncSetAttribute(prune_resident_kernel<TMW, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prune_resident_kernel<TMW, TNW><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p);
+    CK(cudaGetLastError());
+}
+
+template <int TNW>
+void launch_resident_tn(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TM) {
+    case 8: launch_resident_t<8, TNW>(c, p); break;
+    case 9: launch_resident_t<9, TNW>(c, p); break;
+    case 10: launch_resident_t<10, TNW>(c, p); break;
+    case 11: launch_resident_t<11, TNW>(c, p); break;
+    case 12: launch_resident_t<12, TNW>(c, p); break;
+    default: launch_resident_t<13, TNW>(c, p); break;
+    }
+}
+
+void launch_resident(cafe_b200_ctx* c, PruneParams& p)
+{
+    switch (c->TNW) {
+    case 4: launch_resident_tn<4>(c, p); break;
+    case 2: launch_resident_tn<2>(c, p); break;
+    default: launch_resident_tn<1>(c, p); break;
+    }
+}
+
+size_t resident_smem(int tm, int tnw, int N)
+{
+    const int bm = 16 * tm, bn = 32 * tnw;
+    const int vrows = (N + RS_BK - 1) / RS_BK * RS_BK;
+    return sizeof(double) * ((size_t)vrows * (bn + 4) + (size_t)RS_STAGES * RS_BK * (bm + 4) + 2 * PRUNE_THREADS + 2 * RS_STAGES + 2);
+}
+
 // DMMA kernel: column tile BN = 32*TNW; wide tiles halve the matrix traffic per FMA, narrow tiles fill the SMs
 int choose_columns_dmma(cafe_b200_ctx* c, int K)
 {
@@ -302,8 +384,20 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
         tnw >>= 1;
     }
     if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);   // experiment knob
+    // resident kernel when the whole state space is one row pass and Vres + stages fit in shared memory
+    c->prune_kind = 1;
+    if (c->prune_pref == 2 && c->n_mtiles == 1) {
+        int t = tnw;
+        while (t >= 1 && resident_smem(c->TM, t, c->N) > c->smem_optin) t >>= 1;
+        if (t >= 1) { tnw = t; c->prune_kind = 2; }
+    }
     c->TNW = tnw;
     const int bn = 32 * tnw, bm = 16 * c->TM;
+    if (c->prune_kind == 2) {
+        c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+        c->grid = (int)std::min<int64_t>((int64_t)c->n_col_tiles * K, c->n_sms);
+        return bn;
+    }
     const size_t stage = sizeof(double) * (size_t)DM_BK * (bm + 4 + bn + 4);
     const size_t tail = sizeof(double) * (2 * PRUNE_THREADS + 8);
     int stages = (int)((c->smem_optin - tail) / stage);
@@ -391,6 +485,13 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
     CK(cudaGetLastError());
 }
 
+void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
+{
+    if (!c->use_dmma) launch_prune(c, p);
+    else if (c->prune_kind == 2) launch_resident(c, p);
+    else launch_dmma(c, p);
+}
+
 PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
 {
     int bn;
@@ -407,8 +508,12 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     p.prior_d = c->d_prior.p;
     p.logprior = c->d_logprior.p;
     p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
-    c->d_scratch.reserve((size_t)c->grid * c->n_slots * p.slot_stride);
+    const bool resident = c->use_dmma && c->prune_kind == 2;
+    c->d_scratch.reserve((size_t)c->grid * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
     p.scratch = c->d_scratch.p;
+    p.gemm_nodes = c->d_gemm_nodes.p;
+    p.n_gemm = (int)c->gemm_nodes.size();
+    p.n_fslots = c->n_fslots;
     c->d_best.reserve((size_t)K * c->U_stride);
     c->d_ok.reserve((size_t)K * c->U_stride);
     p.out_best = c->d_best.p;
@@ -471,7 +576,7 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
     CK(cudaEventRecord(c->ev[1], c->stream));
     PruneParams p = base_params(c, K, gamma ? MODE_GAMMA : MODE_BASE);
     CK(cudaEventRecord(c->ev[2], c->stream));
-    if (c->use_dmma) launch_dmma(c, p); else launch_prune(c, p);
+    launch_any_prune(c, p);
     CK(cudaEventRecord(c->ev[3], c->stream));
     const int nb = (int)((c->F + FIN_THREADS - 1) / FIN_THREADS);
     c->d_partial.reserve(nb);
@@ -563,7 +668,11 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         CK(cudaGetDeviceProperties(&prop, device));
         c->n_sms = prop.multiProcessorCount;
         c->smem_optin = prop.sharedMemPerBlockOptin;
-        if (const char* e = std::getenv("CAFE_B200_PRUNE")) c->use_dmma = std::string(e) != "dfma";
+        if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
+            const std::string v(e);
+            c->use_dmma = v != "dfma";
+            c->prune_pref = v == "stream" ? 1 : 2;
+        }
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&c->h_result, 2 * sizeof(double)));
@@ -627,6 +736,9 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         CK(cudaMemcpy(c->d_steps.p, c->steps.data(), c->steps.size() * sizeof(Step), cudaMemcpyHostToDevice));
         c->d_children.reserve(c->children.size());
         CK(cudaMemcpy(c->d_children.p, c->children.data(), c->children.size() * sizeof(StepChild), cudaMemcpyHostToDevice));
+        c->d_gemm_nodes.reserve(std::max<size_t>(c->gemm_nodes.size(), 1));
+        if (!c->gemm_nodes.empty())
+            CK(cudaMemcpy(c->d_gemm_nodes.p, c->gemm_nodes.data(), c->gemm_nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 
         // lgamma table with the HOST libm, the same values the reference caches (probability.cpp:69-80)
         c->lg_n = 2 * c->N + 2;
@@ -652,7 +764,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (!c) return CAFE_B200_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_counts_t.release(); c->d_mat_of.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
+    c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
     c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
     c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
@@ -882,7 +994,7 @@ int cafe_b200_root_vectors(cafe_b200_ctx* c, const double* lambdas, int32_t n_la
         PruneParams p = base_params(c, 1, MODE_ROOTS);
         c->d_roots.reserve((size_t)c->U * c->R);
         p.out_roots = c->d_roots.p;
-        if (c->use_dmma) launch_dmma(c, p); else launch_prune(c, p);
+        launch_any_prune(c, p);
         std::vector<double> roots((size_t)c->U * c->R);
         CK(cudaMemcpyAsync(roots.data(), c->d_roots.p, roots.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
