@@ -932,7 +932,9 @@ int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops
         double best = 0.0;
         for (int rep = 0; rep < 6; ++rep) {
             CK(cudaEventRecord(e0));
-            if (use_dmma) dmma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            if (use_dmma == 2) dmma_peak_kernel_k8<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            else if (use_dmma == 3) dmma_peak_kernel_k16<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            else if (use_dmma) dmma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
             else dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
@@ -940,7 +942,10 @@ int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, e0, e1));
             // DFMA: 16 fma per thread-iteration; DMMA: 8 tiles x (8*8*4) fma per warp-iteration
-            double fma_count = use_dmma ? (double)blocks * (threads / 32) * iters * 8.0 * 256.0
+            // m16n8k8: 4 tiles x 1024 fma; m16n8k16: 4 tiles x 2048 fma
+            double fma_count = use_dmma == 2 ? (double)blocks * (threads / 32) * iters * 4.0 * 1024.0
+                             : use_dmma == 3 ? (double)blocks * (threads / 32) * iters * 4.0 * 2048.0
+                             : use_dmma ? (double)blocks * (threads / 32) * iters * 8.0 * 256.0
                                         : (double)blocks * threads * iters * 16.0;
             double tf = 2.0 * fma_count / (ms * 1e-3) / 1e12;
             if (rep > 0 && tf > best) best = tf;

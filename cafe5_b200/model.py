@@ -215,7 +215,7 @@ def measure_fp64_peak(device=0, use_dmma=False):
     """TFLOP/s of the FP64 pipe on `device` (DFMA chains or DMMA tiles), measured by a microbenchmark kernel."""
     lib = _lib.load()
     out = C.c_double()
-    rc = lib.cafe_b200_measure_fp64_peak(int(device), 1 if use_dmma else 0, C.byref(out))
+    rc = lib.cafe_b200_measure_fp64_peak(int(device), int(use_dmma), C.byref(out))
     if rc:
         raise CafeError("measure_fp64_peak: %s" % lib.cafe_b200_last_error(None).decode())
     return out.value

@@ -132,7 +132,7 @@ def test_combine_partials_rejects_failures():
 
 def test_abi_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "cafe_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(cafe_b200_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(cafe_b200_[a-z0-9_]+)\s*\(", header)))
     assert declared == sorted(_lib.SYMBOLS)
     assert os.path.exists(_lib.LIB_PATH), "libcafe_b200.so must be built in-tree (__graft_entry__.build())"
     lib = ctypes.CDLL(_lib.LIB_PATH)

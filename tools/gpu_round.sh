@@ -3,6 +3,7 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv
+timeout 120 python tools/gpu_peaks.py 2>&1 | tee gpurun_out/peaks.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -3 | tee gpurun_out/smoke.log
 timeout 600 python bench.py --steps 8 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json
@@ -13,7 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:prune_ -s 1 -c 1 -f -o gpurun_out/prof_prune \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_prune.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:matrix_gen -s 2 -c 1 -f -o gpurun_out/prof_matrix \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:matrix_gen -s 401 -c 1 -f -o gpurun_out/prof_matrix \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_matrix.log 2>&1
 fi
 ls -la gpurun_out
