@@ -1,10 +1,8 @@
 // cafe_b200.cu -- host side of libcafe_b200.so: context, per-evaluation key planning, launches, C ABI.
 // See include/cafe_b200.h for the boundary and the reference interfaces each entry point replaces.
 #include "../../include/cafe_b200.h"
-#include "kernels.cuh"
-#include "pupko.cuh"
-#include "prune_dmma.cuh"
-#include "prune_resident.cuh"
+#define CAFE_KERNELS_IMPL
+#include "launchers.h"
 #include "peak.cuh"
 
 #include <algorithm>
@@ -22,6 +20,7 @@ using namespace cafe;
 
 namespace {
 
+constexpr int DM_BK_HOST = 16;   // DM_BK of prune_dmma.cuh
 thread_local std::string g_create_error;
 
 struct CudaError { std::string msg; };
@@ -93,14 +92,15 @@ struct cafe_b200_ctx {
 
     // tiling choice
     int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
-    // pruning kernel: 2 = DMMA with the child vector resident in shared memory (default when it fits),
-    // 1 = DMMA streaming both operands (large state spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=resident|stream|dfma
-    int prune_pref = 2, prune_kind = 2;
+    // pruning kernel: 3 = DMMA, resident vector, two alternating column halves per CTA (default when it fits),
+    // 2 = DMMA with the child vector resident in shared memory, 1 = DMMA streaming both operands (large state
+    // spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=duo|resident|stream|dfma
+    int prune_pref = 2, prune_kind = 2, duo_hwn = 4, duo_bk = 8;
     bool use_dmma = true;
     std::vector<int32_t> gemm_nodes;
     int n_fslots = 1;
-    int TNW = 4, dmma_stages = 4;
-    size_t smem_optin = 0;
+    int TNW = 4, WN = 2, resident_wn = 2, dmma_stages = 4;
+    size_t smem_optin = 0, smem_per_sm = 0;
 
     // prior / error model
     bool have_prior = false;
@@ -109,7 +109,8 @@ struct cafe_b200_ctx {
     int em_rows = 0, em_maxcnt = 0;
 
     // device buffers
-    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;
+    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes, d_sm_rank;
+    int stagger_clks = 0;
     DevBuf<int64_t> d_f2u;
     DevBuf<Step> d_steps;
     DevBuf<StepChild> d_children;
@@ -268,137 +269,92 @@ void choose_tiling(cafe_b200_ctx* c)
     }
     c->TM = bestTM;
     c->n_mtiles = bestTiles;
-    c->LD = bestPad;
+    // +4: the arena's row stride equals the kernels' padded shared-memory stride (== 4 mod 16 doubles, conflict-free DMMA fragment
+    // loads), so a whole stage of matrix rows is ONE contiguous, 128-byte aligned bulk copy instead of one copy per row
+    c->LD = bestPad + 4;
 }
 
-template <int TM, int TN>
-void launch_prune_t(cafe_b200_ctx* c, PruneParams& p)
+// shared-memory footprint of prune_resident_kernel<TM, TNW, WN, BK> (ResidentCfg::smem_bytes, prune_resident.cuh)
+size_t resident_stage_bytes(int tm, int bk) { return sizeof(double) * (size_t)bk * (16 * tm + 4); }
+size_t resident_fixed_bytes(int tnw, int wn, int N)
 {
-    using Cfg = PruneCfg<TM, TN>;
-    size_t smem = Cfg::smem_bytes(c->S);
-    CK(cudaFuncSetAttribute(prune_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prune_kernel<TM, TN><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p);
-    CK(cudaGetLastError());
+    const int bn = 8 * tnw * wn, vrows = (N + 7) / 8 * 8;
+    const int parts = std::min(64 * wn / bn, 2);
+    return sizeof(double) * ((size_t)vrows * bn + 2 * parts * bn + 2 * 8);
 }
 
-template <int TN>
-void launch_prune_tn(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TM) {
-    case 8: launch_prune_t<8, TN>(c, p); break;
-    case 9: launch_prune_t<9, TN>(c, p); break;
-    case 10: launch_prune_t<10, TN>(c, p); break;
-    case 11: launch_prune_t<11, TN>(c, p); break;
-    case 12: launch_prune_t<12, TN>(c, p); break;
-    default: launch_prune_t<13, TN>(c, p); break;
-    }
-}
-
-void launch_prune(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TN) {
-    case 4: launch_prune_tn<4>(c, p); break;
-    case 2: launch_prune_tn<2>(c, p); break;
-    default: launch_prune_tn<1>(c, p); break;
-    }
-}
-
-template <int TMW, int TNW>
-void launch_dmma_t(cafe_b200_ctx* c, PruneParams& p)
-{
-    using Cfg = DmmaCfg<TMW, TNW>;
-    size_t smem = Cfg::smem_bytes(c->dmma_stages);
-    CK(cudaFuncSetAttribute(prune_dmma_kernel<TMW, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prune_dmma_kernel<TMW, TNW><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p, c->dmma_stages);
-    CK(cudaGetLastError());
-}
-
-template <int TNW>
-void launch_dmma_tn(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TM) {
-    case 8: launch_dmma_t<8, TNW>(c, p); break;
-    case 9: launch_dmma_t<9, TNW>(c, p); break;
-    case 10: launch_dmma_t<10, TNW>(c, p); break;
-    case 11: launch_dmma_t<11, TNW>(c, p); break;
-    case 12: launch_dmma_t<12, TNW>(c, p); break;
-    default: launch_dmma_t<13, TNW>(c, p); break;
-    }
-}
-
-void launch_dmma(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TNW) {
-    case 4: launch_dmma_tn<4>(c, p); break;
-    case 2: launch_dmma_tn<2>(c, p); break;
-    default: launch_dmma_tn<1>(c, p); break;
-    }
-}
-
-template <int TMW, int TNW>
-void launch_resident_t(cafe_b200_ctx* c, PruneParams& p)
-{
-    using Cfg = ResidentCfg<TMW, TNW>;
-    size_t smem = Cfg::smem_bytes(c->N);
-    CK(cudaFuncSetAttribute(prune_resident_kernel<TMW, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prune_resident_kernel<TMW, TNW><<<c->grid, PRUNE_THREADS, smem, c->stream>>>(p);
-    CK(cudaGetLastError());
-}
-
-template <int TNW>
-void launch_resident_tn(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TM) {
-    case 8: launch_resident_t<8, TNW>(c, p); break;
-    case 9: launch_resident_t<9, TNW>(c, p); break;
-    case 10: launch_resident_t<10, TNW>(c, p); break;
-    case 11: launch_resident_t<11, TNW>(c, p); break;
-    case 12: launch_resident_t<12, TNW>(c, p); break;
-    default: launch_resident_t<13, TNW>(c, p); break;
-    }
-}
-
-void launch_resident(cafe_b200_ctx* c, PruneParams& p)
-{
-    switch (c->TNW) {
-    case 4: launch_resident_tn<4>(c, p); break;
-    case 2: launch_resident_tn<2>(c, p); break;
-    default: launch_resident_tn<1>(c, p); break;
-    }
-}
-
-size_t resident_smem(int tm, int tnw, int N)
-{
-    const int bm = 16 * tm, bn = 32 * tnw;
-    const int vrows = (N + RS_BK - 1) / RS_BK * RS_BK;
-    return sizeof(double) * ((size_t)vrows * (bn + 4) + (size_t)RS_STAGES * RS_BK * (bm + 4) + 2 * PRUNE_THREADS + 2 * RS_STAGES + 2);
-}
-
-// DMMA kernel: column tile BN = 32*TNW; wide tiles halve the matrix traffic per FMA, narrow tiles fill the SMs
+// DMMA kernels: pick the variant and its column tile.  Wide tiles amortise matrix traffic, narrow tiles fill the SMs.
+//   resident, WN = 2: two 128-thread CTAs per SM (BN = 16*TNW, BK = 4)   -- default when it fits
+//   resident, WN = 4: one 256-thread CTA per SM (BN = 32*TNW, BK = 8)
+//   stream          : both operands streamed (any state-space size)
 int choose_columns_dmma(cafe_b200_ctx* c, int K)
 {
+    c->prune_kind = 1;
+    if (c->prune_pref == 3 && c->n_mtiles == 1) {
+        // duo kernel: one CTA per SM, two halves of 8*TNW*HWN columns, one shared matrix ring of 8-row stages
+        const int hwn = c->duo_hwn;
+        int tnw = hwn == 4 ? 2 : 4;
+        while (tnw > 1) {
+            int64_t pairs = ((c->U + 8 * tnw * hwn - 1) / (8 * tnw * hwn)) * K / 2;
+            if (pairs >= 2 * (int64_t)c->n_sms) break;
+            tnw >>= 1;
+        }
+        if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::min(std::atoi(e), hwn == 4 ? 2 : 4);
+        const int vrows = (c->N + 7) / 8 * 8, bn = 8 * tnw * hwn;
+        const size_t fixed = sizeof(double) * ((size_t)2 * vrows * (bn + 4) + 2 * 4 * bn + 2 * 8 + 2);
+        const size_t stage = resident_stage_bytes(c->TM, c->duo_bk);
+        if (fixed + 2 * stage <= c->smem_optin) {
+            int stages = (int)std::min<size_t>((c->smem_optin - fixed) / stage, 8);
+            if (const char* e = std::getenv("CAFE_B200_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));
+            c->prune_kind = 3;
+            c->TNW = tnw;
+            c->dmma_stages = stages;
+            c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+            const int64_t pairs = ((int64_t)c->n_col_tiles * K + 1) / 2;
+            c->grid = (int)std::min<int64_t>(pairs, c->n_sms);
+            return bn;
+        }
+    }
+    if (c->prune_pref >= 2 && c->n_mtiles == 1) {
+        const int wn_first = c->resident_wn;           // 2 (default) or 4 (CAFE_B200_RESIDENT_WN)
+        for (int pass = 0; pass < 2 && c->prune_kind == 1; ++pass) {
+            const int mode = pass == 0 ? wn_first : (wn_first == 4 ? 2 : 4);   // 2: 2 x 128 threads, 4: 1 x 256, 8: 2 x 256 (128 regs)
+            const int wn = mode == 8 ? 4 : mode;
+            const int bk = mode == 4 ? 8 : 4;
+            const int ctas = mode == 4 ? 1 : 2;        // resident CTAs per SM
+            const size_t avail = std::min<size_t>(c->smem_optin, c->smem_per_sm / ctas - 1024);
+            int tnw = mode == 8 ? 2 : 4;
+            while (tnw > 1) {
+                int64_t tiles = ((c->U + 8 * tnw * wn - 1) / (8 * tnw * wn)) * K;
+                if (tiles >= 2 * (int64_t)c->n_sms * ctas) break;
+                tnw >>= 1;
+            }
+            if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::min(std::atoi(e), mode == 8 ? 2 : 4);   // experiment knob
+            const size_t fixed = resident_fixed_bytes(tnw, wn, c->N), stage = resident_stage_bytes(c->TM, bk);
+            if (fixed + 2 * stage > avail) continue;
+            int stages = (int)std::min<size_t>((avail - fixed) / stage, 8);
+            if (const char* e = std::getenv("CAFE_B200_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));
+            c->prune_kind = 2;
+            c->TNW = tnw;
+            c->WN = mode;
+            c->dmma_stages = stages;
+            const int bn = 8 * tnw * wn;
+            c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+            c->grid = (int)std::min<int64_t>((int64_t)c->n_col_tiles * K, (int64_t)c->n_sms * ctas);
+            return bn;
+        }
+    }
     int tnw = 4;
     while (tnw > 1) {
         int64_t tiles = ((c->U + 32 * tnw - 1) / (32 * tnw)) * K;
         if (tiles >= 2 * (int64_t)c->n_sms) break;
         tnw >>= 1;
     }
-    if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);   // experiment knob
-    // resident kernel when the whole state space is one row pass and Vres + stages fit in shared memory
-    c->prune_kind = 1;
-    if (c->prune_pref == 2 && c->n_mtiles == 1) {
-        int t = tnw;
-        while (t >= 1 && resident_smem(c->TM, t, c->N) > c->smem_optin) t >>= 1;
-        if (t >= 1) { tnw = t; c->prune_kind = 2; }
-    }
+    if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);
     c->TNW = tnw;
+    c->WN = 4;
     const int bn = 32 * tnw, bm = 16 * c->TM;
-    if (c->prune_kind == 2) {
-        c->n_col_tiles = (int)((c->U + bn - 1) / bn);
-        c->grid = (int)std::min<int64_t>((int64_t)c->n_col_tiles * K, c->n_sms);
-        return bn;
-    }
-    const size_t stage = sizeof(double) * (size_t)DM_BK * (bm + 4 + bn + 4);
+    const size_t stage = sizeof(double) * (size_t)DM_BK_HOST * (bm + 4 + bn + 4);
     const size_t tail = sizeof(double) * (2 * PRUNE_THREADS + 8);
     int stages = (int)((c->smem_optin - tail) / stage);
     c->dmma_stages = stages > 4 ? 4 : stages;
@@ -487,9 +443,24 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
 
 void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
-    if (!c->use_dmma) launch_prune(c, p);
-    else if (c->prune_kind == 2) launch_resident(c, p);
-    else launch_dmma(c, p);
+    if (!c->use_dmma) CK(launch_prune_dfma(c->TM, c->TN, c->grid, c->S, c->stream, p));
+    else if (c->prune_kind == 3) {
+        if (c->duo_hwn == 4 && c->duo_bk == 4) CK(launch_prune_duo_h4k4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+        else if (c->duo_hwn == 4) CK(launch_prune_duo_h4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+        else CK(launch_prune_duo_h2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+    } else if (c->prune_kind == 2) {
+        p.produce_first = c->WN != 2;
+        if (const char* e = std::getenv("CAFE_B200_PRODUCE_FIRST")) p.produce_first = std::atoi(e);
+        if (c->WN != 4) {
+            c->d_sm_rank.reserve(1024);
+            CK(cudaMemsetAsync(c->d_sm_rank.p, 0, 1024 * sizeof(int32_t), c->stream));
+            p.sm_rank = c->d_sm_rank.p;
+            p.stagger_clks = c->stagger_clks;
+        }
+        if (c->WN == 8) CK(launch_prune_resident_wn4x2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+        else if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+        else CK(launch_prune_resident_wn4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+    } else CK(launch_prune_stream(c->TM, c->TNW, c->grid, c->dmma_stages, c->stream, p));
 }
 
 PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
@@ -508,8 +479,9 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     p.prior_d = c->d_prior.p;
     p.logprior = c->d_logprior.p;
     p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
-    const bool resident = c->use_dmma && c->prune_kind == 2;
-    c->d_scratch.reserve((size_t)c->grid * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
+    const bool resident = c->use_dmma && c->prune_kind >= 2;
+    const int tiles_per_cta = c->use_dmma && c->prune_kind == 3 ? 2 : 1;
+    c->d_scratch.reserve((size_t)c->grid * tiles_per_cta * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
     p.scratch = c->d_scratch.p;
     p.gemm_nodes = c->d_gemm_nodes.p;
     p.n_gemm = (int)c->gemm_nodes.size();
@@ -668,11 +640,16 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         CK(cudaGetDeviceProperties(&prop, device));
         c->n_sms = prop.multiProcessorCount;
         c->smem_optin = prop.sharedMemPerBlockOptin;
+        c->smem_per_sm = prop.sharedMemPerMultiprocessor;
+        if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = (v == 4 || v == 8) ? v : 2; }
+        if (const char* e = std::getenv("CAFE_B200_STAGGER")) c->stagger_clks = std::atoi(e);
         if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
             const std::string v(e);
             c->use_dmma = v != "dfma";
-            c->prune_pref = v == "stream" ? 1 : 2;
+            c->prune_pref = v == "stream" ? 1 : v == "duo" ? 3 : 2;
         }
+        if (const char* e = std::getenv("CAFE_B200_DUO_HWN")) c->duo_hwn = std::atoi(e) == 2 ? 2 : 4;
+        if (const char* e = std::getenv("CAFE_B200_BK")) c->duo_bk = (std::atoi(e) == 4 && c->duo_hwn == 4) ? 4 : 8;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&c->h_result, 2 * sizeof(double)));
@@ -764,7 +741,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (!c) return CAFE_B200_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
+    c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_sm_rank.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
     c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
     c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
@@ -928,7 +905,12 @@ int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+        // bits 8..15 of use_dmma: warps per SM for an issue-rate probe (one CTA per SM); 0 = saturating default
+        const int probe_warps = (use_dmma >> 8) & 0xff;
+        use_dmma &= 0xff;
+        const int iters = 4096;
+        const int blocks = probe_warps ? prop.multiProcessorCount : prop.multiProcessorCount * 8;
+        const int threads = probe_warps ? probe_warps * 32 : 256;
         double best = 0.0;
         for (int rep = 0; rep < 6; ++rep) {
             CK(cudaEventRecord(e0));
@@ -1049,8 +1031,7 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         p.LD = c->LD; p.S = c->S; p.R = c->R; p.N = c->N; p.K = K;
         p.root_len = std::min(c->max_family_size, c->R) + 1;
         p.n_col_tiles = c->n_col_tiles; p.n_mtiles = c->n_mtiles;
-        launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p);
-        CK(cudaGetLastError());
+        CK(launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p));
         const int n = c->n_nodes;
         const size_t Fn = (size_t)c->F * n;
         c->d_cat_probs.reserve(K);

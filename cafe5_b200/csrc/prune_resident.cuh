@@ -27,81 +27,123 @@
 
 namespace cafe {
 
-constexpr int RS_BK = 8;
-constexpr int RS_STAGES = 3;
-
-template <int TMW, int TNW>
+// Geometry: 2 x WN warps (rows x columns); warp tile (8*TMW) x (8*TNW); CTA tile BM = 16*TMW rows x BN = 8*TNW*WN columns.
+//   WN = 4: one 256-thread CTA per SM, BN = 128 (the first version of this kernel: every non-contraction phase -- leaf gathers,
+//           Vres stores, epilogue, pipeline waits -- idles the tensor pipe, 69 % active in profiles/r01_prune_resident_ncu.txt);
+//   WN = 2: 128-thread CTAs with BN = 64 and ~113 KB of shared memory, so TWO CTAs ARE RESIDENT PER SM and one CTA's gathers / stores /
+//           barrier waits overlap the other's DMMA stream (same registers per thread, same accumulators per warp).
+template <int TMW, int TNW, int WN, int BK>
 struct ResidentCfg {
+    static constexpr int THREADS = 64 * WN;
     static constexpr int BM = 16 * TMW;
-    static constexpr int BN = 32 * TNW;
+    static constexpr int BN = 8 * TNW * WN;
     static constexpr int BMP = BM + 4;
-    static constexpr int BNP = BN + 4;
-    static constexpr int STAGE_DOUBLES = RS_BK * BMP;
-    static constexpr int TAIL_DOUBLES = 2 * PRUNE_THREADS + 2 * RS_STAGES + 2;
-    static size_t smem_bytes(int N)   // Vres holds child states [0, S) for the contraction and root rows [1, R] for the epilogue
+    static constexpr int BNP = BN;                 // no padding: columns are XOR-swizzled by (row & 3) << 2 instead
+    static constexpr int STAGE_DOUBLES = BK * BMP;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int PARTS = THREADS / BN < 2 ? THREADS / BN : 2;   // epilogue threads per column
+    static constexpr int TAIL_DOUBLES = 2 * PARTS * BN + 2 * MAX_STAGES;
+    static int vrows(int N) { return (N + 7) / 8 * 8; }   // child states [0, S) for the contraction, root rows [1, R] for the epilogue
+    static size_t smem_bytes(int N, int n_stages)
     {
-        const int vrows = (N + RS_BK - 1) / RS_BK * RS_BK;
-        return sizeof(double) * ((size_t)vrows * BNP + (size_t)RS_STAGES * STAGE_DOUBLES + TAIL_DOUBLES);
+        return sizeof(double) * ((size_t)vrows(N) * BNP + (size_t)n_stages * STAGE_DOUBLES + TAIL_DOUBLES);
     }
 };
 
-template <int TMW, int TNW>
-__global__ void __launch_bounds__(PRUNE_THREADS, 1)
-prune_resident_kernel(const PruneParams p)
+// MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  When MINB > 1 the co-resident CTAs are started out of phase
+// (p.stagger_clks, by their arrival rank on the SM): identical CTAs otherwise run in lockstep, and a CTA's non-contraction phases
+// are only hidden if the other CTA is contracting at that moment.
+template <int TMW, int TNW, int WN, int BK, int MINB>
+__global__ void __launch_bounds__(64 * WN, MINB)
+prune_resident_kernel(const PruneParams p, const int NS)
 {
-    using Cfg = ResidentCfg<TMW, TNW>;
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, BK = RS_BK, NS = RS_STAGES;
+    using Cfg = ResidentCfg<TMW, TNW, WN, BK>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, THREADS = Cfg::THREADS;
+    // Where warp 0 refills the ring: before its own chunk (one more chunk of lead, but it first waits for the slowest warp) or after it.
+    // Measured on B200: "after" wins with one warp per sub-partition and CTA (WN = 2), "before" with two.
+    const bool PRODUCE_FIRST = p.produce_first != 0;
     extern __shared__ __align__(128) double smem_rs[];
     const int kpad = (p.S + BK - 1) / BK * BK;
     const int n_chunks = kpad / BK;
-    const int vrows = (p.N + BK - 1) / BK * BK;
+    const int vrows = (p.N + 7) / 8 * 8;
     double* const Vres = smem_rs;                                     // [vrows][BNP]
     double* const stages = Vres + (size_t)vrows * BNP;                // [NS][BK][BMP]
-    double* const red = stages + (size_t)NS * Cfg::STAGE_DOUBLES;     // [2][PRUNE_THREADS]
-    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(red + 2 * PRUNE_THREADS);
-    uint64_t* const empty_bar = full_bar + NS;
+    double* const red = stages + (size_t)NS * Cfg::STAGE_DOUBLES;     // [2][PARTS*BN]
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(red + 2 * Cfg::PARTS * BN);
+    uint64_t* const empty_bar = full_bar + Cfg::MAX_STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
+    const int wm = warp / WN, wn = warp % WN;         // 2 x WN warps
     const int g = lane >> 2, q = lane & 3;            // DMMA fragment coordinates
     const int row_base = wm * 8 * TMW + g;            // + i*8
     const int col_base = wn * 8 * TNW + 2 * q;        // + j*8 + e
+    // Vres swizzle: element (row, col) lives at column col ^ ((row & 3) << 2).  Rows are a multiple of 16 doubles, so unswizzled the
+    // four k-rows of a DMMA B fragment would hit the same banks; the XOR spreads them over the 32 banks without padding columns
+    // (the 5.6 KB saved per 64-column tile is a fourth pipeline stage).
+    const int swz_g = (g & 3) << 2;                   // rows this thread stores: row & 3 == g & 3
+    const int swz_q = q << 2;                         // rows this thread loads as B fragments: row & 3 == q
     const int n_tiles = p.K * p.n_col_tiles;
     double* const my_slots = p.scratch + (size_t)blockIdx.x * p.n_fslots * p.slot_stride;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, PRUNE_THREADS / 32); }
+        for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        if (MINB > 1 && p.sm_rank != nullptr && p.stagger_clks > 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int rank = atomicAdd(p.sm_rank + (smid & 1023), 1) % MINB;
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)rank * p.stagger_clks) __nanosleep(200);
+        }
     }
     __syncthreads();
 
-    // ---- producer state (warp 0): one continuous stream of matrix chunks over (tile, contraction, chunk) ----
-    unsigned gp = 0;
-    int p_tile = blockIdx.x, p_g = 0, p_chunk = 0;
+    // ---- producer: one continuous stream of matrix chunks over (tile, contraction, chunk).  EVERY warp tracks the cursor (it is a
+    // deterministic function of the chunk count) and the warps take turns issuing the copy, so the ~150 cycles of empty-wait +
+    // expect_tx + UBLKCP per chunk are spread over all sub-partitions instead of making warp 0 the pace-setter; the matrix
+    // pointer is looked up once per contraction, off the per-chunk path. ----
+    constexpr int NW = THREADS / 32;
+    int p_stage = 0;
+    unsigned p_phase = 1;                             // parity to wait for on the empty barrier (first pass: free)
+    int p_tile = blockIdx.x, p_g = 0, p_chunk = 0, p_turn = 0;
+    const double* p_PT = nullptr;
+    auto p_lookup = [&]() {
+        if (p.n_gemm != 0 && p_tile < n_tiles) {
+            const int kcat = p_tile / p.n_col_tiles;
+            p_PT = p.arena + (size_t)p.mat_of[(size_t)kcat * p.n_nodes + p.gemm_nodes[p_g]] * p.LD * p.LD;
+        }
+    };
     auto produce_one = [&]() {
         if (p.n_gemm == 0 || p_tile >= n_tiles) return;
-        const unsigned stage = gp % NS;
-        mbar_wait(empty_bar + stage, ((gp / NS) & 1u) ^ 1u);
-        if (lane < BK) {
-            const int kcat = p_tile / p.n_col_tiles;
-            const int node = p.gemm_nodes[p_g];
-            const double* PT = p.arena + (size_t)p.mat_of[(size_t)kcat * p.n_nodes + node] * p.LD * p.LD;
-            if (lane == 0) mbar_expect_tx(full_bar + stage, (unsigned)(BK * BM * sizeof(double)));
-            __syncwarp(0x000000ffu);
-            bulk_g2s(stages + (size_t)stage * Cfg::STAGE_DOUBLES + lane * BMP,
-                     PT + (size_t)(p_chunk * BK + lane) * p.LD, BM * sizeof(double), full_bar + stage);
+        if (warp == p_turn) {
+            mbar_wait(empty_bar + p_stage, p_phase);
+            if (p.LD == BMP) {                   // arena stride == smem stride: the stage is one contiguous copy
+                if (lane == 0) {
+                    mbar_expect_tx(full_bar + p_stage, (unsigned)(BK * BMP * sizeof(double)));
+                    bulk_g2s(stages + (size_t)p_stage * Cfg::STAGE_DOUBLES, p_PT + (size_t)(p_chunk * BK) * p.LD,
+                             BK * BMP * sizeof(double), full_bar + p_stage);
+                }
+            } else if (lane < BK) {
+                if (lane == 0) mbar_expect_tx(full_bar + p_stage, (unsigned)(BK * BM * sizeof(double)));
+                __syncwarp((1u << BK) - 1u);
+                bulk_g2s(stages + (size_t)p_stage * Cfg::STAGE_DOUBLES + lane * BMP,
+                         p_PT + (size_t)(p_chunk * BK + lane) * p.LD, BM * sizeof(double), full_bar + p_stage);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        ++gp;
+        if (++p_turn == NW) p_turn = 0;
+        if (++p_stage == NS) { p_stage = 0; p_phase ^= 1u; }
         if (++p_chunk == n_chunks) {
             p_chunk = 0;
             if (++p_g == p.n_gemm) { p_g = 0; p_tile += gridDim.x; }
+            p_lookup();
         }
     };
-    if (warp == 0)
-        for (int s = 0; s < NS - 1; ++s) produce_one();
-    unsigned gc = 0;
+    p_lookup();
+    for (int s = 0; s < NS - 1; ++s) produce_one();
+    int c_stage = 0;
+    unsigned c_phase = 0;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int k = tile / p.n_col_tiles;
@@ -177,7 +219,7 @@ prune_resident_kernel(const PruneParams p)
                     const bool live = sp.is_root || row < p.S;
 #pragma unroll
                     for (int j = 0; j < TNW; ++j)
-                        *reinterpret_cast<double2*>(Vres + (size_t)row * BNP + col_base + j * 8) =
+                        *reinterpret_cast<double2*>(Vres + (size_t)row * BNP + ((col_base + j * 8) ^ swz_g)) =
                             live ? make_double2(acc[i][j][0], acc[i][j][1]) : make_double2(0.0, 0.0);
                 }
             }
@@ -190,28 +232,28 @@ prune_resident_kernel(const PruneParams p)
 #pragma unroll
                     for (int j = 0; j < TNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
                 for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                    const unsigned stage = gc % NS;
-                    mbar_wait(full_bar + stage, (gc / NS) & 1u);
-                    const double* As = stages + (size_t)stage * Cfg::STAGE_DOUBLES;
+                    if (PRODUCE_FIRST) produce_one();               // refill the stage the previous chunk released: NS-1 chunks of lead
+                    mbar_wait(full_bar + c_stage, c_phase);
+                    const double* As = stages + (size_t)c_stage * Cfg::STAGE_DOUBLES;
                     const double* Bs = Vres + (size_t)chunk * BK * BNP;
 #pragma unroll
                     for (int k4 = 0; k4 < BK / 4; ++k4) {
                         double a[TMW], b[TNW];
                         const double* ap = As + (k4 * 4 + q) * BMP + row_base;
-                        const double* bp = Bs + (k4 * 4 + q) * BNP + wn * 8 * TNW + g;
+                        const double* bp = Bs + (k4 * 4 + q) * BNP;
 #pragma unroll
                         for (int i = 0; i < TMW; ++i) a[i] = ap[i * 8];
 #pragma unroll
-                        for (int j = 0; j < TNW; ++j) b[j] = bp[j * 8];
+                        for (int j = 0; j < TNW; ++j) b[j] = bp[(wn * 8 * TNW + j * 8 + g) ^ swz_q];
 #pragma unroll
                         for (int i = 0; i < TMW; ++i)
 #pragma unroll
                             for (int j = 0; j < TNW; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar + stage);
-                    ++gc;
-                    if (warp == 0) produce_one();
+                    if (lane == 0) mbar_arrive(empty_bar + c_stage);
+                    if (++c_stage == NS) { c_stage = 0; c_phase ^= 1u; }
+                    if (!PRODUCE_FIRST) produce_one();
                 }
                 // ---- 4. the factor stays in registers for the parent, or is parked once in a global slot ----
                 if (sp.dst_kind == 1) {
@@ -225,34 +267,35 @@ prune_resident_kernel(const PruneParams p)
                 }
             } else {
                 // ---- root epilogue from shared memory: index j <-> root size j+1 (core.cpp:141), weighted by prior(j)
-                constexpr int PARTS = PRUNE_THREADS / BN;
+                constexpr int PARTS = Cfg::PARTS;            // threads beyond PARTS*BN only take part in the barrier
                 const int c = tid % BN, part = tid / BN;
+                const bool active = part < PARTS;
                 const int64_t u = col0 + c;
-                const double* root = Vres + c;
-                double best;
+                double best = 0.0;
                 int any = 0;
-                if (p.mode == MODE_BASE) {
+                if (!active) {
+                } else if (p.mode == MODE_BASE) {
                     best = -INFINITY;           // max_j log L_j + log prior_j   (base_model.cpp:82-91)
                     for (int j = part; j < p.R; j += PARTS) {
-                        const double v = __dadd_rn(log(root[(size_t)(j + 1) * BNP]), p.logprior[j]);
+                        const double v = __dadd_rn(log(Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))]), p.logprior[j]);
                         if (v > best) best = v;
                     }
                 } else if (p.mode == MODE_GAMMA) {
-                    best = 0.0;                 // max_j L_j * prior_j ; failure iff sum_j L_j == 0   (gamma_core.cpp:151-160)
-                    bool first = true;
+                    bool first = true;          // max_j L_j * prior_j ; failure iff sum_j L_j == 0   (gamma_core.cpp:151-160)
                     for (int j = part; j < p.R; j += PARTS) {
-                        const double L = root[(size_t)(j + 1) * BNP];
+                        const double L = Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))];
                         any |= (L != 0.0);
                         const double v = __dmul_rn(L, p.prior_d[j]);
                         if (first || v > best) { best = v; first = false; }
                     }
                 } else {
-                    best = 0.0;
                     if (u < p.U && k == 0)
-                        for (int j = part; j < p.R; j += PARTS) p.out_roots[(size_t)u * p.R + j] = root[(size_t)(j + 1) * BNP];
+                        for (int j = part; j < p.R; j += PARTS) p.out_roots[(size_t)u * p.R + j] = Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))];
                 }
-                red[part * BN + c] = best;
-                red[(PARTS + part) * BN + c] = (double)any;
+                if (active) {
+                    red[part * BN + c] = best;
+                    red[(PARTS + part) * BN + c] = (double)any;
+                }
                 __syncthreads();
                 if (part == 0 && u < p.U && p.mode != MODE_ROOTS) {
                     double bb = red[c];

@@ -171,6 +171,7 @@ pupko_kernel(const PupkoParams p)
     }
 }
 
+#ifdef CAFE_PUPKO_LAUNCH_IMPL   // tu_pupko.cu only
 template <int TM, int TN>
 inline size_t pupko_smem(int S, int n_steps)
 {
@@ -198,7 +199,7 @@ inline void launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const 
     }
 }
 
-inline void launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p)
+inline void launch_pupko_impl(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p)
 {
     switch (TN) {
     case 4: launch_pupko_tn<4>(TM, grid, S, stream, p); break;
@@ -207,6 +208,9 @@ inline void launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, c
     }
 }
 
+#endif  // CAFE_PUPKO_LAUNCH_IMPL
+
+#ifdef CAFE_KERNELS_IMPL
 // Expand unique -> family, fill leaves with observed counts, average the categories
 // (get_weighted_averages, gamma_core.cpp:271-288: val = sum_k p_k * state_k from 0.0, then round, :356).
 __global__ void __launch_bounds__(256)
@@ -237,5 +241,7 @@ expand_states_kernel(const int32_t* __restrict__ st_u, const int64_t* __restrict
     if (!gamma) { states[idx] = last; if (averaged) averaged[idx] = (double)last; }
     else { states[idx] = (int32_t)round(val); if (averaged) averaged[idx] = val; }
 }
+
+#endif  // CAFE_KERNELS_IMPL
 
 }  // namespace cafe
