@@ -368,10 +368,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "family-likelihood evals/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_per_step},
             "gpu_launches": 4 * args.steps,
-            "roofline": {"bound": "fp64", "kernel": "prune_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "peak_source": "FP64 pipe measured live on this GPU by cafe_b200_measure_fp64_peak (DFMA %.2f, DMMA m8n8k4 %.2f TFLOP/s); "
-                                        "MEASURED_PEAKS.json has no FP64 figure" % (peak_dfma, peak_dmma),
+            "roofline": {"bound": "tensor", "kernel": prune_kernel_name(), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                         "peak_source": "FP64 tensor pipe (DMMA; tcgen05 has no FP64 kind) measured live on this GPU by "
+                                        "cafe_b200_measure_fp64_peak: DMMA m8n8k4 %.2f, DFMA %.2f TFLOP/s; MEASURED_PEAKS.json "
+                                        "carries only HBM and bf16 figures" % (peak_dmma, peak_dfma),
                          "alg_flops_per_launch": flops_per_launch, "ms_per_launch": float(np.mean(prune_ms)),
                          "share_of_step": float(np.mean(prune_ms)) / ms_per_step,
                          "matrix_gen": {"ms_per_launch": float(np.mean(mat_ms)), "matrices": n_mats,
@@ -386,6 +387,29 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def prune_kernel_name():
+    return {"dfma": "prune_kernel (DFMA register tiles)", "stream": "prune_dmma_kernel (DMMA, both operands streamed)"}.get(
+        os.environ.get("CAFE_B200_PRUNE", ""), "prune_resident_kernel (FP64 tensor cores: mma.sync.m8n8k4.f64 / DMMA.8x8x4)")
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the pruning kernel in this exact configuration, from the
+    committed `ncu --set full` capture (profiles/r01_prune_resident2_ncu.txt); None when another variant / size is benchmarked."""
+    if os.environ.get("CAFE_B200_PRUNE") or os.environ.get("CAFE_B200_RESIDENT_WN") or sys.argv[1:] and any(
+            a.startswith(("--families", "--taxa", "--cats")) for a in sys.argv[1:]):
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_prune_resident2_ncu.txt")
+    try:
+        total = 0.0
+        for line in open(path):
+            f = [x.strip() for x in line.split("|")]
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return total or None
+    except OSError:
+        return None
 
 
 def matrix_terms(N):

@@ -92,10 +92,9 @@ struct cafe_b200_ctx {
 
     // tiling choice
     int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
-    // pruning kernel: 3 = DMMA, resident vector, two alternating column halves per CTA (default when it fits),
-    // 2 = DMMA with the child vector resident in shared memory, 1 = DMMA streaming both operands (large state
-    // spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=duo|resident|stream|dfma
-    int prune_pref = 2, prune_kind = 2, duo_hwn = 4, duo_bk = 8;
+    // pruning kernel: 2 = DMMA with the child vector resident in shared memory (default when it fits), 1 = DMMA streaming
+    // both operands (large state spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=resident|stream|dfma
+    int prune_pref = 2, prune_kind = 2;
     bool use_dmma = true;
     std::vector<int32_t> gemm_nodes;
     int n_fslots = 1;
@@ -109,8 +108,7 @@ struct cafe_b200_ctx {
     int em_rows = 0, em_maxcnt = 0;
 
     // device buffers
-    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes, d_sm_rank;
-    int stagger_clks = 0;
+    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;
     DevBuf<int64_t> d_f2u;
     DevBuf<Step> d_steps;
     DevBuf<StepChild> d_children;
@@ -290,46 +288,21 @@ size_t resident_fixed_bytes(int tnw, int wn, int N)
 int choose_columns_dmma(cafe_b200_ctx* c, int K)
 {
     c->prune_kind = 1;
-    if (c->prune_pref == 3 && c->n_mtiles == 1) {
-        // duo kernel: one CTA per SM, two halves of 8*TNW*HWN columns, one shared matrix ring of 8-row stages
-        const int hwn = c->duo_hwn;
-        int tnw = hwn == 4 ? 2 : 4;
-        while (tnw > 1) {
-            int64_t pairs = ((c->U + 8 * tnw * hwn - 1) / (8 * tnw * hwn)) * K / 2;
-            if (pairs >= 2 * (int64_t)c->n_sms) break;
-            tnw >>= 1;
-        }
-        if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::min(std::atoi(e), hwn == 4 ? 2 : 4);
-        const int vrows = (c->N + 7) / 8 * 8, bn = 8 * tnw * hwn;
-        const size_t fixed = sizeof(double) * ((size_t)2 * vrows * (bn + 4) + 2 * 4 * bn + 2 * 8 + 2);
-        const size_t stage = resident_stage_bytes(c->TM, c->duo_bk);
-        if (fixed + 2 * stage <= c->smem_optin) {
-            int stages = (int)std::min<size_t>((c->smem_optin - fixed) / stage, 8);
-            if (const char* e = std::getenv("CAFE_B200_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));
-            c->prune_kind = 3;
-            c->TNW = tnw;
-            c->dmma_stages = stages;
-            c->n_col_tiles = (int)((c->U + bn - 1) / bn);
-            const int64_t pairs = ((int64_t)c->n_col_tiles * K + 1) / 2;
-            c->grid = (int)std::min<int64_t>(pairs, c->n_sms);
-            return bn;
-        }
-    }
     if (c->prune_pref >= 2 && c->n_mtiles == 1) {
         const int wn_first = c->resident_wn;           // 2 (default) or 4 (CAFE_B200_RESIDENT_WN)
         for (int pass = 0; pass < 2 && c->prune_kind == 1; ++pass) {
-            const int mode = pass == 0 ? wn_first : (wn_first == 4 ? 2 : 4);   // 2: 2 x 128 threads, 4: 1 x 256, 8: 2 x 256 (128 regs)
-            const int wn = mode == 8 ? 4 : mode;
+            const int mode = pass == 0 ? wn_first : (wn_first == 4 ? 2 : 4);   // 2: two 128-thread CTAs per SM, 4: one 256-thread CTA
+            const int wn = mode;
             const int bk = mode == 4 ? 8 : 4;
             const int ctas = mode == 4 ? 1 : 2;        // resident CTAs per SM
             const size_t avail = std::min<size_t>(c->smem_optin, c->smem_per_sm / ctas - 1024);
-            int tnw = mode == 8 ? 2 : 4;
+            int tnw = 4;
             while (tnw > 1) {
                 int64_t tiles = ((c->U + 8 * tnw * wn - 1) / (8 * tnw * wn)) * K;
                 if (tiles >= 2 * (int64_t)c->n_sms * ctas) break;
                 tnw >>= 1;
             }
-            if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::min(std::atoi(e), mode == 8 ? 2 : 4);   // experiment knob
+            if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);   // experiment knob
             const size_t fixed = resident_fixed_bytes(tnw, wn, c->N), stage = resident_stage_bytes(c->TM, bk);
             if (fixed + 2 * stage > avail) continue;
             int stages = (int)std::min<size_t>((avail - fixed) / stage, 8);
@@ -444,21 +417,8 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
 void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
     if (!c->use_dmma) CK(launch_prune_dfma(c->TM, c->TN, c->grid, c->S, c->stream, p));
-    else if (c->prune_kind == 3) {
-        if (c->duo_hwn == 4 && c->duo_bk == 4) CK(launch_prune_duo_h4k4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
-        else if (c->duo_hwn == 4) CK(launch_prune_duo_h4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
-        else CK(launch_prune_duo_h2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
-    } else if (c->prune_kind == 2) {
-        p.produce_first = c->WN != 2;
-        if (const char* e = std::getenv("CAFE_B200_PRODUCE_FIRST")) p.produce_first = std::atoi(e);
-        if (c->WN != 4) {
-            c->d_sm_rank.reserve(1024);
-            CK(cudaMemsetAsync(c->d_sm_rank.p, 0, 1024 * sizeof(int32_t), c->stream));
-            p.sm_rank = c->d_sm_rank.p;
-            p.stagger_clks = c->stagger_clks;
-        }
-        if (c->WN == 8) CK(launch_prune_resident_wn4x2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
-        else if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+    else if (c->prune_kind == 2) {
+        if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
         else CK(launch_prune_resident_wn4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
     } else CK(launch_prune_stream(c->TM, c->TNW, c->grid, c->dmma_stages, c->stream, p));
 }
@@ -479,9 +439,8 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     p.prior_d = c->d_prior.p;
     p.logprior = c->d_logprior.p;
     p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
-    const bool resident = c->use_dmma && c->prune_kind >= 2;
-    const int tiles_per_cta = c->use_dmma && c->prune_kind == 3 ? 2 : 1;
-    c->d_scratch.reserve((size_t)c->grid * tiles_per_cta * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
+    const bool resident = c->use_dmma && c->prune_kind == 2;
+    c->d_scratch.reserve((size_t)c->grid * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
     p.scratch = c->d_scratch.p;
     p.gemm_nodes = c->d_gemm_nodes.p;
     p.n_gemm = (int)c->gemm_nodes.size();
@@ -641,15 +600,12 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->n_sms = prop.multiProcessorCount;
         c->smem_optin = prop.sharedMemPerBlockOptin;
         c->smem_per_sm = prop.sharedMemPerMultiprocessor;
-        if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = (v == 4 || v == 8) ? v : 2; }
-        if (const char* e = std::getenv("CAFE_B200_STAGGER")) c->stagger_clks = std::atoi(e);
+        if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = v == 4 ? 4 : 2; }
         if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
             const std::string v(e);
             c->use_dmma = v != "dfma";
-            c->prune_pref = v == "stream" ? 1 : v == "duo" ? 3 : 2;
+            c->prune_pref = v == "stream" ? 1 : 2;
         }
-        if (const char* e = std::getenv("CAFE_B200_DUO_HWN")) c->duo_hwn = std::atoi(e) == 2 ? 2 : 4;
-        if (const char* e = std::getenv("CAFE_B200_BK")) c->duo_bk = (std::atoi(e) == 4 && c->duo_hwn == 4) ? 4 : 8;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&c->h_result, 2 * sizeof(double)));
@@ -741,7 +697,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (!c) return CAFE_B200_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_sm_rank.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
+    c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
     c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
     c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();

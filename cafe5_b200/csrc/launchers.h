@@ -14,13 +14,7 @@ cudaError_t launch_prune_stream(int TM, int TNW, int grid, int n_stages, cudaStr
 // DMMA kernel with the child vector resident in shared memory (prune_resident.cuh).
 //   wn4: one 256-thread CTA per SM, BN = 32*TNW, BK = 8;  wn2: two 128-thread CTAs per SM, BN = 16*TNW, BK = 4.
 cudaError_t launch_prune_resident_wn4(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);
-cudaError_t launch_prune_resident_wn4x2(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);   // 2 x 256 threads per SM, TNW <= 2
 cudaError_t launch_prune_resident_wn2(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);
-// DMMA kernel with two column halves per CTA taking the contraction in strict alternation (prune_duo.cuh): BN = 2 x 16*TNW.
-//   h2: halves of 4 warps (256 threads), BNh = 16*TNW, TNW in {1,2,4};  h4: halves of 8 warps (512 threads), BNh = 32*TNW, TNW in {1,2}.
-cudaError_t launch_prune_duo_h2(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);
-cudaError_t launch_prune_duo_h4k4(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);   // 4-row stages
-cudaError_t launch_prune_duo_h4(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p);
 // Pupko reconstruction (pupko.cuh).
 cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p);
 

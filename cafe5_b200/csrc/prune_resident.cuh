@@ -8,9 +8,11 @@
 //        chain child     -> its factor is ALREADY in the registers (it was the previous step's contraction output),
 //        any other child -> its factor is read back from a global "factor slot".
 //   2. V_v is written to a shared-memory tile Vres[S][BN] (never to global memory).
-//   3. W_v = P_v (BM x S) . Vres, FP64 tensor cores (mma.sync.m8n8k4.f64): B fragments come straight from Vres, the
-//      matrix streams through a 3-stage cp.async.bulk + mbarrier pipeline that runs AHEAD ACROSS contractions
-//      (the next node's matrix is known from the schedule), so the tensor pipe never waits for a pipeline fill.
+//   3. W_v = P_v (BM x S) . Vres, FP64 tensor cores (mma.sync.m8n8k4.f64): B fragments come straight from Vres (XOR-swizzled,
+//      no padding columns), the matrix streams through a cp.async.bulk + mbarrier ring that runs AHEAD ACROSS contractions
+//      (the next node's matrix is known from the schedule), so the tensor pipe never waits for a pipeline fill.  The arena's
+//      row stride equals the ring's padded row stride, so a stage is ONE contiguous 128-byte-aligned bulk copy, and the warps
+//      take turns issuing it (a fixed producer warp was the pace-setter of the whole CTA).
 //   4. W_v stays in registers when the parent is the next step (post-order makes that the common case), else it
 //      is stored once to a global factor slot.
 // The root multiplies its children's factors the same way and runs the fused epilogue (prior weighting, max over
@@ -28,10 +30,11 @@
 namespace cafe {
 
 // Geometry: 2 x WN warps (rows x columns); warp tile (8*TMW) x (8*TNW); CTA tile BM = 16*TMW rows x BN = 8*TNW*WN columns.
-//   WN = 4: one 256-thread CTA per SM, BN = 128 (the first version of this kernel: every non-contraction phase -- leaf gathers,
-//           Vres stores, epilogue, pipeline waits -- idles the tensor pipe, 69 % active in profiles/r01_prune_resident_ncu.txt);
-//   WN = 2: 128-thread CTAs with BN = 64 and ~113 KB of shared memory, so TWO CTAs ARE RESIDENT PER SM and one CTA's gathers / stores /
-//           barrier waits overlap the other's DMMA stream (same registers per thread, same accumulators per warp).
+//   WN = 2 (default): 128-thread CTAs with BN = 64 and ~113 KB of shared memory, so TWO CTAs ARE RESIDENT PER SM and one CTA's leaf
+//           gathers / Vres stores / epilogue overlap the other's DMMA stream (same registers per thread and accumulators per warp
+//           as WN = 4).  Tensor pipe 77 % active (profiles/r01_prune_resident2_ncu.txt).
+//   WN = 4: one 256-thread CTA per SM, BN = 128; used when two CTAs do not fit.  Every non-contraction phase idles the tensor
+//           pipe: 69 % active in profiles/r01_prune_resident_ncu.txt.
 template <int TMW, int TNW, int WN, int BK>
 struct ResidentCfg {
     static constexpr int THREADS = 64 * WN;
@@ -50,9 +53,8 @@ struct ResidentCfg {
     }
 };
 
-// MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  When MINB > 1 the co-resident CTAs are started out of phase
-// (p.stagger_clks, by their arrival rank on the SM): identical CTAs otherwise run in lockstep, and a CTA's non-contraction phases
-// are only hidden if the other CTA is contracting at that moment.
+// MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  Co-resident CTAs drift out of phase on their own (starting
+// them half a step apart on purpose changed nothing measurable), so one CTA's leaf gathers / stores overlap the other's DMMA stream.
 template <int TMW, int TNW, int WN, int BK, int MINB>
 __global__ void __launch_bounds__(64 * WN, MINB)
 prune_resident_kernel(const PruneParams p, const int NS)
@@ -61,7 +63,7 @@ prune_resident_kernel(const PruneParams p, const int NS)
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, THREADS = Cfg::THREADS;
     // Where warp 0 refills the ring: before its own chunk (one more chunk of lead, but it first waits for the slowest warp) or after it.
     // Measured on B200: "after" wins with one warp per sub-partition and CTA (WN = 2), "before" with two.
-    const bool PRODUCE_FIRST = p.produce_first != 0;
+    constexpr bool PRODUCE_FIRST = WN != 2;
     extern __shared__ __align__(128) double smem_rs[];
     const int kpad = (p.S + BK - 1) / BK * BK;
     const int n_chunks = kpad / BK;
@@ -89,13 +91,6 @@ prune_resident_kernel(const PruneParams p, const int NS)
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        if (MINB > 1 && p.sm_rank != nullptr && p.stagger_clks > 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            const int rank = atomicAdd(p.sm_rank + (smid & 1023), 1) % MINB;
-            const long long t0 = clock64();
-            while (clock64() - t0 < (long long)rank * p.stagger_clks) __nanosleep(200);
-        }
     }
     __syncthreads();
 

@@ -2,6 +2,5 @@
 #define RS_WN 2
 #define RS_BK 4
 #define RS_MINB 2
-#define RS_MAXTNW 4
 #define RS_ENTRY launch_prune_resident_wn2
 #include "tu_prune_resident.inc"

@@ -10,7 +10,7 @@ timeout 600 python bench.py --steps 8 --warmup 3 2> gpurun_out/bench.err | tee g
 tail -5 gpurun_out/bench.err
 CAFE_B200_PRUNE=dfma timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_dfma.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 396 -c 40 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:prune_ -s 1 -c 1 -f -o gpurun_out/prof_prune \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_prune.log 2>&1
