@@ -16,13 +16,26 @@ SYMBOLS = [
     "cafe_b200_set_error_model", "cafe_b200_eval_base", "cafe_b200_eval_gamma", "cafe_b200_reconstruct",
     "cafe_b200_get_matrix", "cafe_b200_matrix_size", "cafe_b200_root_vectors", "cafe_b200_enqueue_eval",
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
-    "cafe_b200_measure_fp64_peak",
+    "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit",
 ]
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
 c_fp = C.POINTER(C.c_float)
 c_up = C.POINTER(C.c_uint8)
+
+
+class FitOptions(C.Structure):
+    _fields_ = [("n_cat", C.c_int32), ("optimize_epsilon", C.c_int32), ("fixed_alpha", C.c_double), ("fixed_lambdas", c_dp),
+                ("start", c_dp), ("seed", C.c_uint32), ("max_iterations", C.c_int32)]
+
+
+class FitResult(C.Structure):
+    _fields_ = [("values", C.c_double * 16), ("n_values", C.c_int32), ("neg_lnl", C.c_double), ("iterations", C.c_int32),
+                ("evaluations", C.c_int32), ("status", C.c_int32), ("seconds", C.c_double)]
+
+
+OBJECTIVE = C.CFUNCTYPE(C.c_double, c_dp, C.c_void_p)
 
 
 class CTree(C.Structure):
@@ -66,6 +79,10 @@ def load():
     L.cafe_b200_unique_families.restype = C.c_int64
     L.cafe_b200_unique_families.argtypes = [vp]
     L.cafe_b200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, c_dp]
+    L.cafe_b200_describe.argtypes = [vp, C.POINTER(C.c_int64), c_ip, c_ip, c_ip, c_ip, c_dp]
+    L.cafe_b200_discrete_gamma.argtypes = [C.c_int32, C.c_double, c_dp, c_dp]
+    L.cafe_b200_minimize.argtypes = [OBJECTIVE, C.c_void_p, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, c_ip]
+    L.cafe_b200_fit.argtypes = [vp, C.POINTER(FitOptions), C.POINTER(FitResult)]
     _lib = L
     return L
 

@@ -849,6 +849,19 @@ int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matri
 
 int64_t cafe_b200_unique_families(const cafe_b200_ctx* c) { return c ? c->U : 0; }
 
+int cafe_b200_describe(const cafe_b200_ctx* c, int64_t* n_families, int32_t* n_nodes, int32_t* n_lambda_classes,
+                       int32_t* max_family_size, int32_t* max_root_family_size, double* longest_branch)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    if (n_families) *n_families = c->F;
+    if (n_nodes) *n_nodes = c->n_nodes;
+    if (n_lambda_classes) *n_lambda_classes = c->n_lambda_classes;
+    if (max_family_size) *max_family_size = c->max_family_size;
+    if (max_root_family_size) *max_root_family_size = c->R;
+    if (longest_branch) *longest_branch = *std::max_element(c->branch_length.begin(), c->branch_length.end());
+    return CAFE_B200_OK;
+}
+
 int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops)
 {
     try {

@@ -204,11 +204,57 @@ class Context:
     def stream(self):
         return self.lib.cafe_b200_stream(self.h)
 
+    def describe(self):
+        nf = C.c_int64()
+        nn, nl, mfs, mrs = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        lb = C.c_double()
+        self._check(self.lib.cafe_b200_describe(self.h, C.byref(nf), C.byref(nn), C.byref(nl), C.byref(mfs), C.byref(mrs), C.byref(lb)), "describe")
+        return dict(n_families=nf.value, n_nodes=nn.value, n_lambda_classes=nl.value, max_family_size=mfs.value,
+                    max_root_family_size=mrs.value, longest_branch=lb.value)
+
+    def fit(self, n_cat=0, optimize_epsilon=False, fixed_alpha=0.0, fixed_lambdas=None, start=None, seed=10, max_iterations=0):
+        """optimizer::optimize over the scorer the reference would build (lambda | lambda, epsilon | lambda, alpha | alpha):
+        the library's C++ host driver (cafe5_b200/host/fit.cpp) running Nelder-Mead over eval_base / eval_gamma."""
+        o = _lib.FitOptions()
+        o.n_cat, o.optimize_epsilon, o.fixed_alpha = int(n_cat), 1 if optimize_epsilon else 0, float(fixed_alpha)
+        fl = _lib.as_f64(fixed_lambdas) if fixed_lambdas is not None else None
+        st = _lib.as_f64(start) if start is not None else None
+        o.fixed_lambdas, o.start = _lib.dp(fl), _lib.dp(st)
+        o.seed, o.max_iterations = int(seed), int(max_iterations)
+        r = _lib.FitResult()
+        self._check(self.lib.cafe_b200_fit(self.h, C.byref(o), C.byref(r)), "fit")
+        return dict(values=np.array(r.values[:r.n_values]), neg_lnl=r.neg_lnl, iterations=r.iterations, evaluations=r.evaluations,
+                    status=r.status, seconds=r.seconds)
+
     def last_stats(self):
         nl, nm = C.c_int32(), C.c_int32()
         a, b = C.c_float(), C.c_float()
         self._check(self.lib.cafe_b200_last_stats(self.h, C.byref(nl), C.byref(nm), C.byref(a), C.byref(b)), "last_stats")
         return dict(launches=nl.value, matrices=nm.value, ms_matrices=a.value, ms_prune=b.value)
+
+
+def discrete_gamma(n_cat, alpha):
+    """(cat_probs, multipliers) from the library's C++ host implementation of get_gamma (cafe5_b200/host/discrete_gamma.hpp)."""
+    lib = _lib.load()
+    p, m = np.zeros(n_cat), np.zeros(n_cat)
+    rc = lib.cafe_b200_discrete_gamma(int(n_cat), float(alpha), _lib.dp(p), _lib.dp(m))
+    if rc:
+        raise CafeError("discrete_gamma: bad argument")
+    return list(p), list(m)
+
+
+def minimize(fn, x0, max_iterations=300):
+    """The library's simplex search (cafe5_b200/host/nelder_mead.hpp) over a Python objective: (x, f, iterations)."""
+    lib = _lib.load()
+    n = len(x0)
+    cb = _lib.OBJECTIVE(lambda x, _u: float(fn([x[i] for i in range(n)])))
+    x0 = _lib.as_f64(x0)
+    out = np.zeros(n)
+    f, it = C.c_double(), C.c_int32()
+    rc = lib.cafe_b200_minimize(cb, None, n, _lib.dp(x0), int(max_iterations), _lib.dp(out), C.byref(f), C.byref(it))
+    if rc:
+        raise CafeError("minimize: bad argument")
+    return out, f.value, it.value
 
 
 def measure_fp64_peak(device=0, use_dmma=False):

@@ -102,6 +102,43 @@ int cafe_b200_reconstruct(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_l
                           const double* multipliers, const double* cat_probs, int32_t n_cat,
                           int32_t* cat_states, int32_t* states, double* averaged);
 
+/* Host driver -------------------------------------------------------- */
+
+/* Shape of a context: what get_lambda_optimizer reads from the model (longest branch: src/base_model.cpp:117-118). */
+int cafe_b200_describe(const cafe_b200_ctx* ctx, int64_t* n_families, int32_t* n_nodes, int32_t* n_lambda_classes,
+                       int32_t* max_family_size, int32_t* max_root_family_size, double* longest_branch);
+
+/* get_gamma (src/gamma.cpp:225-241): K equiprobable categories, multipliers = rescaled category medians. */
+int cafe_b200_discrete_gamma(int32_t n_cat, double alpha, double* cat_probs, double* multipliers);
+
+/* The reference's simplex search (fminsearch_min, src/optimizer.cpp:287-322) over an arbitrary objective. */
+int cafe_b200_minimize(double (*objective)(const double* x, void* user), void* user, int32_t n, const double* x0,
+                       int32_t max_iterations, double* x_out, double* f_out, int32_t* iterations);
+
+#define CAFE_B200_FIT_MAX_VALUES 16
+typedef struct {
+    int32_t n_cat;                /* <= 1: base model; > 1: gamma model with n_cat categories */
+    int32_t optimize_epsilon;     /* base model with the default error model and epsilon as a free parameter (`-e` without a file) */
+    double fixed_alpha;           /* gamma model: > 0 keeps alpha fixed (`-k` with a given alpha) */
+    const double* fixed_lambdas;  /* non-NULL: lambdas are given (one per class), only alpha is estimated */
+    const double* start;          /* non-NULL: explicit start point instead of the seeded random guess */
+    uint32_t seed;                /* std::mt19937 seed of the initial guess (the reference never seeds its engine) */
+    int32_t max_iterations;       /* <= 0: the reference's 300 */
+} cafe_b200_fit_options;
+typedef struct {
+    double values[CAFE_B200_FIT_MAX_VALUES];   /* lambdas..., then alpha or epsilon */
+    int32_t n_values;
+    double neg_lnl;
+    int32_t iterations;           /* simplex iterations (optimizer::result::num_iterations) */
+    int32_t evaluations;          /* calls of infer_family_likelihoods (event_monitor attempts) */
+    int32_t status;               /* 0 converged, 1 no finite starting point (OptimizerInitializationFailure), 2 iteration cap */
+    double seconds;
+} cafe_b200_fit_result;
+
+/* optimizer::optimize (src/optimizer.cpp:540-569) over the scorer get_lambda_optimizer would build
+ * (src/base_model.cpp:111-131, src/gamma_core.cpp:239-269); set_prior (and set_error_model for a fixed error model) first. */
+int cafe_b200_fit(cafe_b200_ctx* ctx, const cafe_b200_fit_options* options, cafe_b200_fit_result* result);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

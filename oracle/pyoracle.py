@@ -288,6 +288,18 @@ class RefLib:
     def max_threads(self):
         return self.lib.ref_max_threads()
 
+    def fminsearch(self, fn, x0, max_iterations=300):
+        """The reference's fminsearch_min (src/optimizer.cpp:287-322) over a Python objective."""
+        CB = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
+        n = len(x0)
+        cb = CB(lambda x, _u: float(fn([x[i] for i in range(n)])))
+        self.lib.ref_fminsearch.argtypes = [CB, C.c_void_p, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_ip]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        out = np.zeros(n)
+        f, it = C.c_double(), C.c_int()
+        self._check(self.lib.ref_fminsearch(cb, None, n, _dp(x0), int(max_iterations), _dp(out), C.byref(f), C.byref(it)))
+        return out, f.value, it.value
+
     def flatten(self, newick, lambda_newick=None):
         n = self.lib.ref_tree_node_count(newick.encode())
         if n < 0:

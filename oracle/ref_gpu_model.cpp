@@ -96,3 +96,34 @@ int ref_optimize(void* h, int backend, int n_cat, int optimize_epsilon, unsigned
 const char* ref_ctx_error(void* h) { return ((ref_ctx_view*)h)->err.c_str(); }
 
 }  // extern "C"
+
+// ---- the reference's fminsearch over an arbitrary C callback: pins the product's simplex search (cafe5_b200/host/nelder_mead.hpp) ----
+namespace {
+class callback_scorer : public optimizer_scorer {
+    double (*_cb)(const double*, void*);
+    void* _user;
+    std::vector<double> _x0;
+public:
+    callback_scorer(double (*cb)(const double*, void*), void* user, const double* x0, int n) : _cb(cb), _user(user), _x0(x0, x0 + n) {}
+    std::vector<double> initial_guesses() override { return _x0; }
+    double calculate_score(const double* values) override { return _cb(values, _user); }
+};
+}
+
+extern "C" int ref_fminsearch(double (*cb)(const double*, void*), void* user, int n, const double* x0, int max_iterations,
+                              double* x_out, double* f_out, int* iterations)
+{
+    try {
+        callback_scorer scorer(cb, user, x0, n);
+        FMinSearch* pfm = fminsearch_new_with_eq(&scorer, n);
+        pfm->maxiters = max_iterations > 0 ? max_iterations : 300;   // optimizer_parameters::neldermead_iterations
+        std::vector<double> start(x0, x0 + n);
+        fminsearch_min(pfm, start.data());
+        candidate* best = get_best_result(pfm);
+        for (int i = 0; i < n; ++i) x_out[i] = best->values[i];
+        *f_out = best->score;
+        *iterations = pfm->iters;
+        fminsearch_free(pfm);
+        return 0;
+    } catch (std::exception&) { return 1; }
+}

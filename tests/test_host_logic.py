@@ -149,3 +149,41 @@ def test_create_fails_loudly_without_a_gpu():
     t = FlatTree("(A:1,B:1);")
     with pytest.raises(CafeError):
         Context(t, np.array([[1, 2]], dtype=np.int32), 56, 8)
+
+
+# ---- C++ host driver pieces of libcafe_b200.so that need no GPU (cafe5_b200/host/) ------------------------------
+
+def test_cpp_discrete_gamma_matches_python_and_reference(ref):
+    from cafe5_b200.model import discrete_gamma
+    for K in (1, 2, 3, 4, 8):
+        for alpha in (0.05, 0.3, 0.62731793802343, 0.65, 1.0, 2.5, 17.0):
+            p, m = discrete_gamma(K, alpha)
+            pp, mp = get_gamma(K, alpha)
+            pr, mr = ref.get_gamma(K, alpha)
+            assert p == pp and m == mp, (K, alpha)
+            assert np.array_equal(m, mr) and np.array_equal(p, pr), (K, alpha)
+
+
+def _rosenbrock(x):
+    return (1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+
+
+def _walled(x):
+    """A surface with an infinite wall (like a rejected parameter vector) and a flat tie region."""
+    if x[0] <= 0 or x[1] > 3:
+        return math.inf
+    return abs(x[0] - 0.7) + round((x[1] - 1.3) ** 2, 3)
+
+
+@pytest.mark.parametrize("fn,x0", [(_rosenbrock, [-1.2, 1.0]), (_rosenbrock, [0.0, 0.0]), (_walled, [0.002, 1.0]),
+                                   (lambda x: (x[0] - 0.0018) ** 2 * 1e6 + 3.0, [0.0021]),
+                                   (lambda x: sum((v - i) ** 2 for i, v in enumerate(x)), [0.5, 0.0, -1.0])])
+def test_cpp_nelder_mead_follows_the_reference_fminsearch(ref, fn, x0):
+    """Same objective, same start: the product's simplex search must visit the same points as fminsearch_min
+    (src/optimizer.cpp:287-322) -- identical evaluation trace, iteration count and result, bit for bit."""
+    from cafe5_b200.model import minimize
+    trace_ref, trace_ours = [], []
+    xr, fr, itr = ref.fminsearch(lambda x: (trace_ref.append(tuple(x)), fn(x))[1], x0)
+    xo, fo, ito = minimize(lambda x: (trace_ours.append(tuple(x)), fn(x))[1], x0)
+    assert trace_ours == trace_ref
+    assert ito == itr and fo == fr and np.array_equal(xo, xr)

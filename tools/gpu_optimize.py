@@ -1,0 +1,28 @@
+"""Wall time of a whole parameter optimisation (BASELINE configs 1 and 2) with the REFERENCE's own optimizer
+(src/optimizer.cpp, compiled unmodified into oracle/_ref) driving either the reference's CPU models or the CUDA
+models through cafe5_b200/host/gpu_model.hpp.  Development / measurement script (uses oracle/, like the tests)."""
+import os, sys, time, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cafe5_b200 import families as fam
+from oracle.pyoracle import RefLib
+
+g = np.load(os.path.join(ROOT, "tests", "golden", "mammals.npz"))
+species = [str(s) for s in g["species"]]
+counts = g["counts"].astype(np.int32)
+mfs, mrs = int(g["max_family_size"]), int(g["max_root_family_size"])
+ref = RefLib()
+ctx = ref.ctx(str(g["newick"]), species, counts, mfs, mrs, fam.uniform_prior(mrs))
+out = {"threads": ref.max_threads(), "families": int(counts.shape[0])}
+for name, kw, backends in (("config1_base", dict(n_cat=0), ("gpu", "cpu")), ("config2_gamma_k4", dict(n_cat=4), ("gpu",))):
+    for b in backends:
+        if b == "cpu" and os.environ.get("SKIP_CPU"):
+            continue
+        t = time.time()
+        r = ctx.optimize(b, seed=10, **kw)
+        r["wall_s"] = time.time() - t
+        r["values"] = [float(v) for v in r["values"]]
+        out["%s_%s" % (name, b)] = r
+        print(name, b, json.dumps(r), flush=True)
+print(json.dumps(out))
