@@ -25,4 +25,18 @@ for name, kw, backends in (("config1_base", dict(n_cat=0), ("gpu", "cpu")), ("co
         r["values"] = [float(v) for v in r["values"]]
         out["%s_%s" % (name, b)] = r
         print(name, b, json.dumps(r), flush=True)
+# the product's own host driver (cafe_b200_fit) on the same data, same seed
+from cafe5_b200.model import Context
+from cafe5_b200.tree import FlatTree
+tree = FlatTree(str(g["newick"]), species=species)
+pctx = Context(tree, counts, mfs, mrs)
+pctx.set_prior(fam.uniform_prior(mrs))
+for name, kw in (("config1_base", dict(n_cat=0)), ("config2_gamma_k4", dict(n_cat=4)), ("config1_base_epsilon", dict(n_cat=0, optimize_epsilon=True))):
+    t = time.time()
+    r = pctx.fit(seed=10, **kw)
+    r["wall_s"] = time.time() - t
+    r["values"] = [float(v) for v in r["values"]]
+    out["%s_product" % name] = r
+    print(name, "product driver", json.dumps(r), flush=True)
+pctx.close()
 print(json.dumps(out))

@@ -8,13 +8,13 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -3 | tee gpurun_out/smoke.log
 timeout 600 python bench.py --steps 8 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
-CAFE_B200_PRUNE=dfma timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_dfma.json
+CAFE_B200_PRUNE=dfma timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-fit 2>/dev/null | tee gpurun_out/bench_dfma.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 396 -c 40 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fit > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:prune_ -s 1 -c 1 -f -o gpurun_out/prof_prune \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_prune.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fit > gpurun_out/ncu_prune.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:matrix_gen -s 401 -c 1 -f -o gpurun_out/prof_matrix \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_matrix.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fit > gpurun_out/ncu_matrix.log 2>&1
 fi
 ls -la gpurun_out
