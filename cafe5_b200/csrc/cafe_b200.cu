@@ -97,6 +97,7 @@ struct cafe_b200_ctx {
     int prune_pref = 2, prune_kind = 2;
     bool use_dmma = true;
     std::vector<int32_t> gemm_nodes;
+    InlineSchedule sched{};                // schedule + key index as a kernel parameter (resident kernel)
     int n_fslots = 1;
     int TNW = 4, WN = 2, resident_wn = 2, dmma_stages = 4;
     size_t smem_optin = 0, smem_per_sm = 0;
@@ -388,8 +389,36 @@ KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* m
     return kp;
 }
 
+void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
+{
+    InlineSchedule& s = c->sched;
+    const size_t n_steps = c->steps.size(), n_children = c->children.size();
+    const size_t words = n_steps * 9 + n_children * 5 + kp.mat_of.size() + c->gemm_nodes.size();
+    s.valid = 0;
+    if (words > (size_t)SCHED_WORDS || kp.mat_of.size() != (kp.mat_of.size() / c->n_nodes) * (size_t)c->n_nodes) return;
+    int o = 0;
+    for (const Step& st : c->steps) {
+        const int32_t f[9] = {st.node, st.is_root, st.out_slot, st.n_children, st.child_begin, st.parent_step, st.carry_in, st.dst_kind, st.f_slot};
+        memcpy(s.w + o, f, sizeof f);
+        o += 9;
+    }
+    s.off_children = o;
+    for (const StepChild& ch : c->children) {
+        const int32_t f[5] = {ch.node, ch.leaf_row, ch.slot, ch.kind, ch.f_slot};
+        memcpy(s.w + o, f, sizeof f);
+        o += 5;
+    }
+    s.off_mat_of = o;
+    memcpy(s.w + o, kp.mat_of.data(), kp.mat_of.size() * sizeof(int32_t));
+    o += (int)kp.mat_of.size();
+    s.off_gemm = o;
+    if (!c->gemm_nodes.empty()) memcpy(s.w + o, c->gemm_nodes.data(), c->gemm_nodes.size() * sizeof(int32_t));
+    s.valid = 1;
+}
+
 void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp)
 {
+    fill_inline_schedule(c, kp);
     size_t n_mats = kp.params.size();
     size_t arena = n_mats * (size_t)c->LD * c->LD;
     if (arena > c->d_arena.cap) {
@@ -418,8 +447,8 @@ void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
     if (!c->use_dmma) CK(launch_prune_dfma(c->TM, c->TN, c->grid, c->S, c->stream, p));
     else if (c->prune_kind == 2) {
-        if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
-        else CK(launch_prune_resident_wn4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p));
+        if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
+        else CK(launch_prune_resident_wn4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
     } else CK(launch_prune_stream(c->TM, c->TNW, c->grid, c->dmma_stages, c->stream, p));
 }
 

@@ -57,7 +57,7 @@ struct ResidentCfg {
 // them half a step apart on purpose changed nothing measurable), so one CTA's leaf gathers / stores overlap the other's DMMA stream.
 template <int TMW, int TNW, int WN, int BK, int MINB>
 __global__ void __launch_bounds__(64 * WN, MINB)
-prune_resident_kernel(const PruneParams p, const int NS)
+prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__ InlineSchedule sched)
 {
     using Cfg = ResidentCfg<TMW, TNW, WN, BK>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, THREADS = Cfg::THREADS;
@@ -106,7 +106,9 @@ prune_resident_kernel(const PruneParams p, const int NS)
     auto p_lookup = [&]() {
         if (p.n_gemm != 0 && p_tile < n_tiles) {
             const int kcat = p_tile / p.n_col_tiles;
-            p_PT = p.arena + (size_t)p.mat_of[(size_t)kcat * p.n_nodes + p.gemm_nodes[p_g]] * p.LD * p.LD;
+            const int node = sched.valid ? sched.w[sched.off_gemm + p_g] : p.gemm_nodes[p_g];
+            const int mat = sched.valid ? sched.w[sched.off_mat_of + kcat * p.n_nodes + node] : p.mat_of[(size_t)kcat * p.n_nodes + node];
+            p_PT = p.arena + (size_t)mat * p.LD * p.LD;
         }
     };
     auto produce_one = [&]() {
@@ -147,15 +149,26 @@ prune_resident_kernel(const PruneParams p, const int NS)
         double acc[TMW][TNW][2];
 
         for (int st = 0; st < p.n_steps; ++st) {
-            const Step sp = p.steps[st];
+            Step sp;
+            if (sched.valid) {
+                const int o = st * 9;
+                sp.node = sched.w[o]; sp.is_root = sched.w[o + 1]; sp.out_slot = sched.w[o + 2]; sp.n_children = sched.w[o + 3];
+                sp.child_begin = sched.w[o + 4]; sp.parent_step = sched.w[o + 5]; sp.carry_in = sched.w[o + 6];
+                sp.dst_kind = sched.w[o + 7]; sp.f_slot = sched.w[o + 8];
+            } else sp = p.steps[st];
             bool has_acc = sp.carry_in != 0;
             // ---- 1. V_v = product of the children's factors (probability.cpp:215-217, 229-231) ----
             for (int ci = 0; ci < sp.n_children; ++ci) {
-                const StepChild ch = p.children[sp.child_begin + ci];
+                StepChild ch;
+                if (sched.valid) {
+                    const int o = sched.off_children + (sp.child_begin + ci) * 5;
+                    ch.node = sched.w[o]; ch.leaf_row = sched.w[o + 1]; ch.slot = sched.w[o + 2]; ch.kind = sched.w[o + 3]; ch.f_slot = sched.w[o + 4];
+                } else ch = p.children[sp.child_begin + ci];
                 if (ch.kind == 1) continue;                       // carried: already in acc
                 if (ch.kind == 0) {
                     // leaf: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
-                    const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
+                    const int mat = sched.valid ? sched.w[sched.off_mat_of + k * p.n_nodes + ch.node] : mat_of[ch.node];
+                    const double* __restrict__ PT = p.arena + (size_t)mat * p.LD * p.LD;
 #pragma unroll
                     for (int j = 0; j < TNW; ++j)
 #pragma unroll
@@ -220,6 +233,21 @@ prune_resident_kernel(const PruneParams p, const int NS)
             }
             __syncthreads();
 
+            // The next step's leaf counts come from DRAM (the count table is streamed once per category): pull their lines into L2 now, a
+            // whole contraction ahead of the gather that needs them.
+            if (sched.valid && tid < 2) {
+                int nst = st + 1, ntile = tile;
+                if (nst == p.n_steps) { nst = 0; ntile += gridDim.x; }
+                if (ntile < n_tiles) {
+                    const int64_t ncol = (int64_t)(ntile % p.n_col_tiles) * BN + tid * 32;
+                    const int o = nst * 9, nch = sched.w[o + 3], cb = sched.w[o + 4];
+                    for (int ci = 0; ci < nch; ++ci) {
+                        const int lr = sched.w[sched.off_children + (cb + ci) * 5 + 1];
+                        if (lr >= 0 && ncol < p.U_stride)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.counts_t + (size_t)lr * p.U_stride + ncol));
+                    }
+                }
+            }
             if (!sp.is_root) {
                 // ---- 3. W_v = P_v . V_v on the FP64 tensor cores (matrix_cache.cpp:49-56) ----
 #pragma unroll

@@ -39,4 +39,23 @@ for name, kw in (("config1_base", dict(n_cat=0)), ("config2_gamma_k4", dict(n_ca
     out["%s_product" % name] = r
     print(name, "product driver", json.dumps(r), flush=True)
 pctx.close()
+# config 3: error model from file + two lambda classes (chimp/human separate); config 4: Hymenoptera, gamma K=8
+from cafe5_b200.model import error_model
+tree3 = FlatTree(str(g["newick"]), str(g["lambda_newick"]), species=species)
+pctx = Context(tree3, counts, mfs, mrs)
+pctx.set_prior(fam.uniform_prior(mrs))
+pctx.set_error_model(error_model(g["em_probs"], int(g["em_maxcnt"])))
+t = time.time(); r = pctx.fit(seed=10, n_cat=0); r["wall_s"] = time.time() - t; r["values"] = [float(v) for v in r["values"]]
+out["config3_errormodel_two_lambdas_product"] = r
+print("config3_errormodel_two_lambdas product driver", json.dumps(r), flush=True)
+pctx.close()
+h = np.load(os.path.join(ROOT, "tests", "golden", "hymenoptera.npz"))
+treeh = FlatTree(str(h["newick"]), species=[str(x) for x in h["species"]])
+hm, hr = int(h["max_family_size"]), int(h["max_root_family_size"])
+pctx = Context(treeh, h["counts"].astype(np.int32), hm, hr)
+pctx.set_prior(fam.uniform_prior(hr))
+t = time.time(); r = pctx.fit(seed=10, n_cat=8); r["wall_s"] = time.time() - t; r["values"] = [float(v) for v in r["values"]]
+out["config4_hymenoptera_gamma_k8_product"] = r
+print("config4_hymenoptera_gamma_k8 product driver", json.dumps(r), flush=True)
+pctx.close()
 print(json.dumps(out))
