@@ -348,15 +348,33 @@ def run_ours(args):
     # ---------------- wall time of one whole (lambda, alpha) optimisation (the metric's second half) ----------------
     # the library's own host driver (cafe_b200_fit: seeded start, Nelder-Mead with the reference's constants) on this shard
     fit = None
-    if world == 1 and not args.no_fit:
-        t0 = time.perf_counter()
+    if not args.no_fit:
         # explicit start: with 125,000 families on 118 branches the reference's random start (normal(0.002 L, 0.2) / L) is usually
         # rejected by the all-or-nothing rule (one underflowed family => +inf), for the reference exactly as for us
-        r = ctx.fit(n_cat=K, start=[1.5 * LAMBDA0, 1.0])
+        start = [1.5 * LAMBDA0, 1.0]
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            r = ctx.fit(n_cat=K, start=start)
+            how = "cafe_b200_fit (C++ host driver)"
+        else:
+            from cafe5_b200.model import discrete_gamma
+
+            def local_score(v):   # this rank's shard; the ranks exchange 24 bytes per evaluation inside fit_sharded
+                if not (v[1] > 0):
+                    return math.inf, 0
+                cp_i, mu_i = discrete_gamma(K, v[1])
+                o = ctx.eval_gamma([v[0]], v[1], mu_i, cp_i, want_family=False)
+                return o["neg_lnl"], o["n_failed"]
+
+            r = cdist.fit_sharded(local_score, start)
+            r["status"] = 0
+            how = "cafe5_b200.dist.fit_sharded (the same simplex search on every rank over the all-gathered score)"
+        barrier()
         fit = {"wall_s": time.perf_counter() - t0, "iterations": r["iterations"], "evaluations": r["evaluations"], "status": r["status"],
                "lambda": float(r["values"][0]), "alpha": float(r["values"][1]), "neg_lnl": r["neg_lnl"],
-               "what": "cafe_b200_fit: gamma K=%d, (lambda, alpha) estimated by Nelder-Mead (tolx = tolf = 1e-6, reference constants) "
-                       "over %d families from the start point (1.5 x true lambda, alpha = 1)" % (K, counts.shape[0])}
+               "what": "%s: gamma K=%d, (lambda, alpha) estimated by Nelder-Mead (tolx = tolf = 1e-6, reference constants) over %d "
+                       "families from the start point (1.5 x true lambda, alpha = 1)" % (how, K, counts.shape[0] * world)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -51,3 +51,24 @@ def allreduce_score(neg_lnl, n_failed, group=None):
     if rows[:, 2].any():
         return math.inf, int(rows[:, 1].sum())
     return combine_partials([(r[0], r[1]) for r in rows])
+
+
+def fit_sharded(local_score, start, max_iterations=300, group=None):
+    """Parameter search over a family table sharded across ranks: every rank runs the library's simplex search
+    (cafe_b200_minimize, cafe5_b200/host/nelder_mead.hpp) over the SAME objective -- its own shard's partial
+    (-lnL, n_failed) from `local_score(values)` combined with every other rank's by `allreduce_score`.  The combined score
+    is bit-identical on every rank (fixed-order sum), so all ranks take the same simplex decisions and stay in step with
+    no other communication: one 24-byte exchange per likelihood evaluation.
+
+    local_score(values) -> (neg_lnl_partial, n_failed).  Returns dict(values, neg_lnl, iterations, evaluations)."""
+    from .model import minimize
+    n_eval = [0]
+
+    def objective(x):
+        n_eval[0] += 1
+        neg, nf = local_score(list(x))
+        total, _ = allreduce_score(neg, nf, group)
+        return total
+
+    x, f, it = minimize(objective, list(start), max_iterations)
+    return dict(values=x, neg_lnl=f, iterations=it, evaluations=n_eval[0])

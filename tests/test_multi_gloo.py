@@ -72,3 +72,63 @@ def test_two_rank_sharded_score(fail):
     else:
         whole = o.eval_gamma(tree, _counts(), 60, 45, prior, [0.01], [0.5, 1.5], [0.5, 0.5])
         assert abs(results[0][1] - whole["neg_lnl"]) <= 1e-13 * whole["neg_lnl"] and results[0][2] == 0
+
+
+def _fit_worker(rank, world, port, out_queue):
+    import torch.distributed as dist
+    from oracle.pyoracle import OracleLib
+    from cafe5_b200.gamma import get_gamma
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = OracleLib()
+    o.set_threads(1)
+    tree = FlatTree(NEWICK)
+    counts = _counts()
+    lo, hi = cdist.shard_bounds(counts.shape[0], world, rank)
+    prior = fam.uniform_prior(45)
+
+    def local_score(v):   # the oracle stands in for the GPU context of this rank (no GPU in the CPU suite)
+        if v[0] <= 0 or v[1] <= 0:
+            return math.inf, 0
+        cp, mu = get_gamma(2, v[1])
+        r = o.eval_gamma(tree, counts[lo:hi], 60, 45, prior, [v[0]], mu, cp, alpha=v[1])
+        return r["neg_lnl"], r["n_failed"]
+
+    r = cdist.fit_sharded(local_score, [0.01, 1.0], max_iterations=25)
+    out_queue.put((rank, tuple(r["values"]), r["neg_lnl"], r["iterations"], r["evaluations"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_fit_matches_single_rank():
+    """Sharded optimisation: both ranks walk the same simplex; the result equals the unsharded search to rounding of the
+    two-term partial sum."""
+    from oracle.pyoracle import OracleLib
+    from cafe5_b200.gamma import get_gamma
+    from cafe5_b200.model import minimize
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][1:] == results[1][1:]              # identical trajectory and result on every rank
+    o = OracleLib()
+    tree = FlatTree(NEWICK)
+    prior = fam.uniform_prior(45)
+    counts = _counts()
+
+    def whole(v):
+        if v[0] <= 0 or v[1] <= 0:
+            return math.inf
+        cp, mu = get_gamma(2, v[1])
+        return o.eval_gamma(tree, counts, 60, 45, prior, [v[0]], mu, cp, alpha=v[1])["neg_lnl"]
+
+    x, f, it = minimize(whole, [0.01, 1.0], 25)
+    assert it == results[0][3]
+    assert np.allclose(x, results[0][1], rtol=1e-9) and abs(f - results[0][2]) <= 1e-11 * f

@@ -58,4 +58,27 @@ t = time.time(); r = pctx.fit(seed=10, n_cat=8); r["wall_s"] = time.time() - t; 
 out["config4_hymenoptera_gamma_k8_product"] = r
 print("config4_hymenoptera_gamma_k8 product driver", json.dumps(r), flush=True)
 pctx.close()
+# Pupko reconstruction (row a13) wall times through the host API (all states copied back)
+from cafe5_b200.gamma import get_gamma
+cp, mu = get_gamma(4, 0.65)
+pctx = Context(tree, counts, mfs, mrs)
+pctx.set_prior(fam.uniform_prior(mrs))
+for label, args in (("base", ([0.0018], None, None)), ("gamma_k4", ([0.0018], mu, cp))):
+    pctx.reconstruct(*args)
+    t = time.time(); pctx.reconstruct(*args); dt = time.time() - t
+    out["pupko_mammals_%s_s" % label] = dt
+    print("pupko mammals %s: %.4f s for %d families" % (label, dt, counts.shape[0]), flush=True)
+pctx.close()
+from cafe5_b200.synthetic import make_tree_newick, simulate_families
+t60 = FlatTree(make_tree_newick(60, seed=20261017))
+boot = Context(t60, np.ones((1, t60.n_leaves), dtype=np.int32), 170, 150)
+c60 = simulate_families(t60, 125000, 0.002, mu, boot.get_matrix, seed=20261017)
+boot.close()
+pctx = Context(t60, c60, 170, 150)
+pctx.set_prior(fam.uniform_prior(150))
+pctx.reconstruct([0.002], mu, cp)
+t = time.time(); pctx.reconstruct([0.002], mu, cp); dt = time.time() - t
+out["pupko_config5_shard_gamma_k4_s"] = dt
+print("pupko config-5 shard (125000 families, 60 taxa, K=4): %.3f s" % dt, flush=True)
+pctx.close()
 print(json.dumps(out))
