@@ -308,6 +308,7 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
             if (fixed + 2 * stage > avail) continue;
             int stages = (int)std::min<size_t>((avail - fixed) / stage, 8);
             if (const char* e = std::getenv("CAFE_B200_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));
+            stages = std::max(2, std::min(stages, (c->S + bk - 1) / bk + 1));   // the prefill never reaches past the first matrix
             c->prune_kind = 2;
             c->TNW = tnw;
             c->WN = mode;
