@@ -382,7 +382,6 @@ def run_ours(args):
                 return o["neg_lnl"], o["n_failed"]
 
             r = cdist.fit_sharded(local_score, start)
-            r["status"] = 0
             how = "cafe5_b200.dist.fit_sharded (the same simplex search on every rank over the all-gathered score)"
         barrier()
         fit = {"wall_s": time.perf_counter() - t0, "iterations": r["iterations"], "evaluations": r["evaluations"], "status": r["status"],

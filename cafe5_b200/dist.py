@@ -60,7 +60,7 @@ def fit_sharded(local_score, start, max_iterations=300, group=None):
     is bit-identical on every rank (fixed-order sum), so all ranks take the same simplex decisions and stay in step with
     no other communication: one 24-byte exchange per likelihood evaluation.
 
-    local_score(values) -> (neg_lnl_partial, n_failed).  Returns dict(values, neg_lnl, iterations, evaluations)."""
+    local_score(values) -> (neg_lnl_partial, n_failed).  Returns dict(values, neg_lnl, iterations, evaluations, status)."""
     from .model import minimize
     n_eval = [0]
 
@@ -71,4 +71,5 @@ def fit_sharded(local_score, start, max_iterations=300, group=None):
         return total
 
     x, f, it = minimize(objective, list(start), max_iterations)
-    return dict(values=x, neg_lnl=f, iterations=it, evaluations=n_eval[0])
+    # status as cafe_b200_fit reports it: 0 converged (tolx and tolf 1e-6), 2 stopped at the iteration cap
+    return dict(values=x, neg_lnl=f, iterations=it, evaluations=n_eval[0], status=2 if it >= max_iterations else 0)
