@@ -234,46 +234,7 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
             if (sp.is_root) {
                 // ---- root epilogue: index j <-> root size j+1 (core.cpp:141), weighted by prior(j)
                 __syncthreads();
-                constexpr int PARTS = PRUNE_THREADS / BN;
-                const int c = tid % BN, part = tid / BN;
-                const int64_t u = col0 + c;
-                const double* root = out_slot + c;
-                double best;
-                int any = 0;
-                if (p.mode == MODE_BASE) {
-                    best = -INFINITY;           // max_j log L_j + log prior_j   (base_model.cpp:82-91)
-                    for (int j = part; j < p.R; j += PARTS) {
-                        const double v = __dadd_rn(log(root[(size_t)(j + 1) * BN]), p.logprior[j]);
-                        if (v > best) best = v;
-                    }
-                } else if (p.mode == MODE_GAMMA) {
-                    best = 0.0;                 // max_j L_j * prior_j ; failure iff sum_j L_j == 0   (gamma_core.cpp:151-160)
-                    bool first = true;
-                    for (int j = part; j < p.R; j += PARTS) {
-                        const double L = root[(size_t)(j + 1) * BN];
-                        any |= (L != 0.0);
-                        const double v = __dmul_rn(L, p.prior_d[j]);
-                        if (first || v > best) { best = v; first = false; }
-                    }
-                } else {
-                    best = 0.0;
-                    if (u < p.U && k == 0)
-                        for (int j = part; j < p.R; j += PARTS) p.out_roots[(size_t)u * p.R + j] = root[(size_t)(j + 1) * BN];
-                }
-                red[part * BN + c] = best;
-                red[(PARTS + part) * BN + c] = (double)any;
-                __syncthreads();
-                if (part == 0 && u < p.U && p.mode != MODE_ROOTS) {
-                    double bb = red[c];
-                    int aa = red[PARTS * BN + c] != 0.0;
-                    for (int qq = 1; qq < PARTS; ++qq) {
-                        const double v = red[qq * BN + c];
-                        if (v > bb) bb = v;
-                        aa |= red[(PARTS + qq) * BN + c] != 0.0;
-                    }
-                    p.out_best[(size_t)k * p.U_stride + u] = bb;
-                    if (p.mode == MODE_GAMMA) p.out_ok[(size_t)k * p.U_stride + u] = (uint8_t)aa;
-                }
+                root_epilogue<BN, PRUNE_THREADS / BN, false>(p, out_slot, BN, red, tid, k, col0);
             }
             __syncthreads();   // the slot just written is read by a later step
         }

@@ -290,47 +290,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                 }
             } else {
                 // ---- root epilogue from shared memory: index j <-> root size j+1 (core.cpp:141), weighted by prior(j)
-                constexpr int PARTS = Cfg::PARTS;            // threads beyond PARTS*BN only take part in the barrier
-                const int c = tid % BN, part = tid / BN;
-                const bool active = part < PARTS;
-                const int64_t u = col0 + c;
-                double best = 0.0;
-                int any = 0;
-                if (!active) {
-                } else if (p.mode == MODE_BASE) {
-                    best = -INFINITY;           // max_j log L_j + log prior_j   (base_model.cpp:82-91)
-                    for (int j = part; j < p.R; j += PARTS) {
-                        const double v = __dadd_rn(log(Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))]), p.logprior[j]);
-                        if (v > best) best = v;
-                    }
-                } else if (p.mode == MODE_GAMMA) {
-                    bool first = true;          // max_j L_j * prior_j ; failure iff sum_j L_j == 0   (gamma_core.cpp:151-160)
-                    for (int j = part; j < p.R; j += PARTS) {
-                        const double L = Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))];
-                        any |= (L != 0.0);
-                        const double v = __dmul_rn(L, p.prior_d[j]);
-                        if (first || v > best) { best = v; first = false; }
-                    }
-                } else {
-                    if (u < p.U && k == 0)
-                        for (int j = part; j < p.R; j += PARTS) p.out_roots[(size_t)u * p.R + j] = Vres[(size_t)(j + 1) * BNP + (c ^ (((j + 1) & 3) << 2))];
-                }
-                if (active) {
-                    red[part * BN + c] = best;
-                    red[(PARTS + part) * BN + c] = (double)any;
-                }
-                __syncthreads();
-                if (part == 0 && u < p.U && p.mode != MODE_ROOTS) {
-                    double bb = red[c];
-                    int aa = red[PARTS * BN + c] != 0.0;
-                    for (int qq = 1; qq < PARTS; ++qq) {
-                        const double v = red[qq * BN + c];
-                        if (v > bb) bb = v;
-                        aa |= red[(PARTS + qq) * BN + c] != 0.0;
-                    }
-                    p.out_best[(size_t)k * p.U_stride + u] = bb;
-                    if (p.mode == MODE_GAMMA) p.out_ok[(size_t)k * p.U_stride + u] = (uint8_t)aa;
-                }
+                root_epilogue<BN, Cfg::PARTS, true>(p, Vres, BNP, red, tid, k, col0);
             }
         }
         __syncthreads();   // factor slots of this tile are dead; Vres / red are reused by the next tile
