@@ -68,6 +68,50 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Leaf child of a pruning step, in DMMA-fragment layout (shared by prune_dmma_kernel and prune_resident_kernel):
+//   factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202; no error model: the single column P(s -> obs))
+// multiplied into (or, for the first child, copied to) the accumulators.  rows: PT + first_row + i*8 for the thread's TMW row
+// tiles; columns: col0 + col_base + j*8 + e.  Gathers of the TRANSPOSED matrix: row `obs` is contiguous in s.
+template <int TMW, int TNW>
+__device__ __forceinline__ void leaf_factor_into(double (&acc)[TMW][TNW][2], bool has_acc, const PruneParams& p,
+                                                 const double* __restrict__ PT, int leaf_row, int first_row, int64_t col0, int col_base)
+{
+#pragma unroll
+    for (int j = 0; j < TNW; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int64_t u = col0 + col_base + j * 8 + e;
+            if (u >= p.U) u = p.U - 1;                    // padding columns replay the last family; never written out
+            const int obs = p.counts_t[(size_t)leaf_row * p.U_stride + u];
+            if (p.em == nullptr) {
+                const double* __restrict__ r = PT + (size_t)obs * p.LD + first_row;
+#pragma unroll
+                for (int i = 0; i < TMW; ++i) {
+                    const double v = __ldg(r + i * 8);
+                    acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], v) : v;
+                }
+            } else {
+                const int er = obs < p.em_rows ? obs : p.em_rows - 1;
+                double pe[3];
+                const double* r[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int idx = obs - 1 + d;
+                    const bool ok = idx >= 0 && idx < p.S;
+                    pe[d] = ok ? __ldg(p.em + er * 3 + d) : 0.0;
+                    r[d] = PT + (size_t)(ok ? idx : obs) * p.LD + first_row;
+                }
+#pragma unroll
+                for (int i = 0; i < TMW; ++i) {
+                    double f = __dmul_rn(__ldg(r[0] + i * 8), pe[0]);       // c ascending, separately rounded
+                    f = __dadd_rn(f, __dmul_rn(__ldg(r[1] + i * 8), pe[1]));
+                    f = __dadd_rn(f, __dmul_rn(__ldg(r[2] + i * 8), pe[2]));
+                    acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], f) : f;
+                }
+            }
+        }
+}
+
 template <int TMW, int TNW>
 __global__ void __launch_bounds__(PRUNE_THREADS, 1)
 prune_dmma_kernel(const PruneParams p, const int n_stages)
@@ -114,41 +158,7 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
                     const StepChild ch = p.children[sp.child_begin + ci];
                     const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
                     if (ch.leaf_row >= 0) {
-                        // ---- leaf child: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
-#pragma unroll
-                        for (int j = 0; j < TNW; ++j)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                int64_t u = col0 + col_base + j * 8 + e;
-                                if (u >= p.U) u = p.U - 1;     // padding columns replay the last family; never written out
-                                const int obs = p.counts_t[(size_t)ch.leaf_row * p.U_stride + u];
-                                if (p.em == nullptr) {
-                                    const double* __restrict__ r = PT + (size_t)obs * p.LD + m0 + row_base;
-#pragma unroll
-                                    for (int i = 0; i < TMW; ++i) {
-                                        const double v = __ldg(r + i * 8);
-                                        acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], v) : v;
-                                    }
-                                } else {
-                                    const int er = obs < p.em_rows ? obs : p.em_rows - 1;
-                                    double pe[3];
-                                    const double* r[3];
-#pragma unroll
-                                    for (int d = 0; d < 3; ++d) {
-                                        const int idx = obs - 1 + d;
-                                        const bool ok = idx >= 0 && idx < p.S;
-                                        pe[d] = ok ? __ldg(p.em + er * 3 + d) : 0.0;
-                                        r[d] = PT + (size_t)(ok ? idx : obs) * p.LD + m0 + row_base;
-                                    }
-#pragma unroll
-                                    for (int i = 0; i < TMW; ++i) {
-                                        double f = __dmul_rn(__ldg(r[0] + i * 8), pe[0]);       // c ascending, separately rounded
-                                        f = __dadd_rn(f, __dmul_rn(__ldg(r[1] + i * 8), pe[1]));
-                                        f = __dadd_rn(f, __dmul_rn(__ldg(r[2] + i * 8), pe[2]));
-                                        acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], f) : f;
-                                    }
-                                }
-                            }
+                        leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ch.leaf_row, m0 + row_base, col0, col_base);
                     } else {
                         // ---- internal child: acc = P[m0.., 0..S) . V_child   (matrix_cache.cpp:49-56)
                         if (has_acc) {   // park the running product in the output slot while the tiles accumulate

@@ -169,40 +169,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     // leaf: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
                     const int mat = sched.valid ? sched.w[sched.off_mat_of + k * p.n_nodes + ch.node] : mat_of[ch.node];
                     const double* __restrict__ PT = p.arena + (size_t)mat * p.LD * p.LD;
-#pragma unroll
-                    for (int j = 0; j < TNW; ++j)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            int64_t u = col0 + col_base + j * 8 + e;
-                            if (u >= p.U) u = p.U - 1;            // padding columns replay the last family; never written out
-                            const int obs = p.counts_t[(size_t)ch.leaf_row * p.U_stride + u];
-                            if (p.em == nullptr) {
-                                const double* __restrict__ r = PT + (size_t)obs * p.LD + row_base;
-#pragma unroll
-                                for (int i = 0; i < TMW; ++i) {
-                                    const double v = __ldg(r + i * 8);
-                                    acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], v) : v;
-                                }
-                            } else {
-                                const int er = obs < p.em_rows ? obs : p.em_rows - 1;
-                                double pe[3];
-                                const double* r[3];
-#pragma unroll
-                                for (int d = 0; d < 3; ++d) {
-                                    const int idx = obs - 1 + d;
-                                    const bool ok = idx >= 0 && idx < p.S;
-                                    pe[d] = ok ? __ldg(p.em + er * 3 + d) : 0.0;
-                                    r[d] = PT + (size_t)(ok ? idx : obs) * p.LD + row_base;
-                                }
-#pragma unroll
-                                for (int i = 0; i < TMW; ++i) {
-                                    double f = __dmul_rn(__ldg(r[0] + i * 8), pe[0]);       // c ascending, separately rounded
-                                    f = __dadd_rn(f, __dmul_rn(__ldg(r[1] + i * 8), pe[1]));
-                                    f = __dadd_rn(f, __dmul_rn(__ldg(r[2] + i * 8), pe[2]));
-                                    acc[i][j][e] = has_acc ? __dmul_rn(acc[i][j][e], f) : f;
-                                }
-                            }
-                        }
+                    leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ch.leaf_row, row_base, col0, col_base);
                 } else {
                     // factor of an earlier sibling subtree, parked in a global slot
                     const double* __restrict__ fs = my_slots + (size_t)ch.f_slot * p.slot_stride;

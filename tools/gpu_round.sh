@@ -18,3 +18,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:matr
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fit > gpurun_out/ncu_matrix.log 2>&1
 fi
 ls -la gpurun_out
+# every kernel variant through the parity tests (the default run above exercises only the geometry the host picks)
+for v in "CAFE_B200_PRUNE=dfma" "CAFE_B200_PRUNE=stream" "CAFE_B200_RESIDENT_WN=4"; do
+  echo "== $v"; env $v timeout 400 python -m pytest tests -m gpu -x -q -k "config1 or config2 or small_trees or cliff or config3 or randomized or config5" 2>&1 | tail -2 | tee -a gpurun_out/pytest_gpu_variants.log
+done
