@@ -4,6 +4,7 @@
 #define CAFE_KERNELS_IMPL
 #include "launchers.h"
 #include "peak.cuh"
+#include "simulate.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1051,6 +1052,72 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         d2h(c, cat_states, c->d_cat_states_f.p, Fn * K);
         d2h(c, averaged, c->d_avg_f.p, Fn);
         CK(cudaStreamSynchronize(c->stream));
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
+                       int32_t n_cat, int32_t max_sim, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
+                       int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || n_lambda < c->n_lambda_classes || !root_sizes || n_families <= 0 || !counts) throw CudaError{"ARG: bad argument"};
+        if (n_cat > 0 && (!multipliers || !cat_probs)) throw CudaError{"ARG: gamma simulation needs multipliers and cat_probs"};
+        if (max_sim < 2 || max_sim > c->N) throw CudaError{"RANGE: max_sim must be in [2, matrix size]"};
+        CK(cudaSetDevice(c->device));
+        const int K = n_cat > 0 ? n_cat : 1;
+        static const double one = 1.0;
+        const double* mult = n_cat > 0 ? multipliers : &one;
+        const double* probs = n_cat > 0 ? cat_probs : &one;
+        KeyPlan kp = plan_keys(c, lambdas, mult, K);
+        upload_plan(c, kp);
+        const int n_mats = (int)kp.params.size();
+        launch_matrices(c, n_mats);
+        const int n = c->n_nodes;
+        const size_t F = (size_t)n_families;
+        DevBuf<double> d_cdf, d_probs;
+        DevBuf<int32_t> d_parent, d_leaf_col, d_root, d_sizes, d_counts, d_cat;
+        DevBuf<uint8_t> d_has;
+        DevBuf<unsigned long long> d_exh;
+        struct Release {   // scratch of one call: freed on every exit path
+            DevBuf<double>&a, &b; DevBuf<int32_t>&c1, &c2, &c3, &c4, &c5, &c6; DevBuf<uint8_t>& d; DevBuf<unsigned long long>& e;
+            ~Release() { a.release(); b.release(); c1.release(); c2.release(); c3.release(); c4.release(); c5.release(); c6.release(); d.release(); e.release(); }
+        } release{d_cdf, d_probs, d_parent, d_leaf_col, d_root, d_sizes, d_counts, d_cat, d_has, d_exh};
+        d_cdf.reserve((size_t)n_mats * max_sim * c->N);
+        d_probs.reserve(K);
+        d_parent.reserve(n); d_leaf_col.reserve(n);
+        d_root.reserve(F); d_sizes.reserve(F * n); d_counts.reserve(F * c->n_species); d_cat.reserve(F);
+        d_has.reserve(F * n);
+        d_exh.reserve(1, true);
+        CK(cudaMemcpyAsync(d_probs.p, probs, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_parent.p, c->parent.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_leaf_col.p, c->leaf_col.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_root.p, root_sizes, F * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(d_counts.p, 0, F * c->n_species * sizeof(int32_t), c->stream));
+        sim_cdf_kernel<<<n_mats, 256, 0, c->stream>>>(c->d_arena.p, c->LD, c->N, max_sim, d_cdf.p);
+        CK(cudaGetLastError());
+        SimParams sp{};
+        sp.parent = d_parent.p; sp.leaf_col = d_leaf_col.p; sp.mat_of = c->d_mat_of.p; sp.cdf = d_cdf.p; sp.cat_probs = d_probs.p;
+        sp.root_sizes = d_root.p; sp.sizes = d_sizes.p; sp.has = d_has.p; sp.counts = d_counts.p; sp.categories = d_cat.p;
+        sp.exhausted = d_exh.p; sp.F = n_families; sp.seed = seed;
+        sp.n_nodes = n; sp.n_species = c->n_species; sp.K = K; sp.N = c->N; sp.max_sim = max_sim;
+        simulate_kernel<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>(sp);
+        CK(cudaGetLastError());
+        d2h(c, counts, d_counts.p, F * c->n_species);
+        d2h(c, categories, d_cat.p, F);
+        unsigned long long exhausted = 0;
+        CK(cudaMemcpyAsync(&exhausted, d_exh.p, sizeof exhausted, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<int32_t> sizes_t;
+        if (node_sizes) {
+            sizes_t.resize(F * n);
+            CK(cudaMemcpyAsync(sizes_t.data(), d_sizes.p, F * n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        if (node_sizes)
+            for (size_t f = 0; f < F; ++f)
+                for (int i = 0; i < n; ++i) node_sizes[f * n + i] = sizes_t[(size_t)i * F + f];
+        if (n_not_at_root) *n_not_at_root = (int64_t)exhausted;
         return CAFE_B200_OK;
     } catch (const CudaError& e) { return fail(c, e); }
 }

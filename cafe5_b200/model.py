@@ -204,6 +204,23 @@ class Context:
     def stream(self):
         return self.lib.cafe_b200_stream(self.h)
 
+    def simulate(self, lambdas, root_sizes, multipliers=None, cat_probs=None, max_sim=120, seed=1, want_nodes=False):
+        """Simulate len(root_sizes) families on this context's tree (cafe_b200_simulate): dict(counts[F, n_species],
+        categories[F], node_sizes[F, n_nodes] or None, n_not_at_root)."""
+        lam = _lib.as_f64(lambdas)
+        K = 0 if multipliers is None else len(multipliers)
+        mu = None if K == 0 else _lib.as_f64(multipliers)
+        cp = None if K == 0 else _lib.as_f64(cat_probs)
+        roots = np.ascontiguousarray(root_sizes, dtype=np.int32)
+        F = roots.shape[0]
+        counts = np.zeros((F, self.n_species), dtype=np.int32)
+        cats = np.zeros(F, dtype=np.int32)
+        nodes = np.zeros((F, self.n_nodes), dtype=np.int32) if want_nodes else None
+        bad = C.c_int64()
+        self._check(self.lib.cafe_b200_simulate(self.h, _lib.dp(lam), len(lam), _lib.dp(mu), _lib.dp(cp), K, int(max_sim), _lib.ip(roots),
+                                                F, int(seed), _lib.ip(counts), _lib.ip(nodes), _lib.ip(cats), C.byref(bad)), "simulate")
+        return dict(counts=counts, categories=cats, node_sizes=nodes, n_not_at_root=bad.value)
+
     def describe(self):
         nf = C.c_int64()
         nn, nl, mfs, mrs = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()

@@ -139,6 +139,17 @@ typedef struct {
  * (src/base_model.cpp:111-131, src/gamma_core.cpp:239-269); set_prior (and set_error_model for a fixed error model) first. */
 int cafe_b200_fit(cafe_b200_ctx* ctx, const cafe_b200_fit_options* options, cafe_b200_fit_result* result);
 
+/* Simulator: simulator::create_trial (src/simulator.cpp:29-58) for n_families families on the context's
+ * tree.  root_sizes[f] is the root size of family f (the reference reads its vectorised root distribution at index f); child sizes
+ * are drawn from matrix rows restricted to sizes < max_sim (select_random_y, src/matrix_cache.cpp:60-66; the reference passes its
+ * max_family_size, 120 by default); n_cat > 0: each family first picks a rate category with cat_probs (gamma_core.cpp:91-95).
+ * counts[F x n_species] (the context's species columns); node_sizes[F x n_nodes] and categories[F] optional; n_not_at_root:
+ * families still absent at the root after 50 redraws (kept, as the reference keeps them with a warning).  Counter-based RNG
+ * (Philox4x32-10 keyed by seed, one stream per family): reproducible per seed, distributional parity with the reference. */
+int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
+                       int32_t n_cat, int32_t max_sim, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
+                       int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after
