@@ -16,7 +16,7 @@ SYMBOLS = [
     "cafe_b200_set_error_model", "cafe_b200_eval_base", "cafe_b200_eval_gamma", "cafe_b200_reconstruct",
     "cafe_b200_get_matrix", "cafe_b200_matrix_size", "cafe_b200_root_vectors", "cafe_b200_enqueue_eval",
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
-    "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit", "cafe_b200_simulate",
+    "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit", "cafe_b200_simulate", "cafe_b200_pvalues",
 ]
 
 c_dp = C.POINTER(C.c_double)
@@ -83,7 +83,8 @@ def load():
     L.cafe_b200_discrete_gamma.argtypes = [C.c_int32, C.c_double, c_dp, c_dp]
     L.cafe_b200_minimize.argtypes = [OBJECTIVE, C.c_void_p, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, c_ip]
     L.cafe_b200_fit.argtypes = [vp, C.POINTER(FitOptions), C.POINTER(FitResult)]
-    L.cafe_b200_simulate.argtypes = [vp, c_dp, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_ip, C.c_int64, C.c_uint64,
+    L.cafe_b200_pvalues.argtypes = [vp, c_dp, C.c_int32, C.c_int32, C.c_uint64, c_dp]
+    L.cafe_b200_simulate.argtypes = [vp, c_dp, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, C.c_int32, c_ip, C.c_int64, C.c_uint64,
                                      c_ip, c_ip, c_ip, C.POINTER(C.c_int64)]
     _lib = L
     return L

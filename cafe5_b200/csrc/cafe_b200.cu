@@ -1057,7 +1057,7 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
 }
 
 int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
-                       int32_t n_cat, int32_t max_sim, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
+                       int32_t n_cat, int32_t max_sim, int32_t max_redraws, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
                        int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root)
 {
     if (!c) return CAFE_B200_ERR_ARG;
@@ -1102,6 +1102,7 @@ int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda
         sp.root_sizes = d_root.p; sp.sizes = d_sizes.p; sp.has = d_has.p; sp.counts = d_counts.p; sp.categories = d_cat.p;
         sp.exhausted = d_exh.p; sp.F = n_families; sp.seed = seed;
         sp.n_nodes = n; sp.n_species = c->n_species; sp.K = K; sp.N = c->N; sp.max_sim = max_sim;
+        sp.max_attempts = 1 + std::max(max_redraws, 0);
         simulate_kernel<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>(sp);
         CK(cudaGetLastError());
         d2h(c, counts, d_counts.p, F * c->n_species);
@@ -1120,6 +1121,68 @@ int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda
         if (n_not_at_root) *n_not_at_root = (int64_t)exhausted;
         return CAFE_B200_OK;
     } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    cafe_b200_ctx* sim = nullptr;
+    try {
+        if (!lambdas || n_lambda < c->n_lambda_classes || n_sims < 1 || !pvalues) throw CudaError{"ARG: bad argument"};
+        if (!c->have_prior) throw CudaError{"STATE: set_prior must be called first"};
+        const int R = c->R, n = c->n_nodes;
+        // 1. conditional distributions: n_sims families per root size 1..R, no redraws, no error model (get_random_probabilities,
+        //    create_family: src/probability.cpp:355-375,434-447), child sizes below max_family_size
+        const size_t Fs = (size_t)R * n_sims;
+        std::vector<int32_t> roots(Fs), sim_counts(Fs * c->n_species);
+        for (int r = 0; r < R; ++r) std::fill(roots.begin() + (size_t)r * n_sims, roots.begin() + (size_t)(r + 1) * n_sims, r + 1);
+        int rc = cafe_b200_simulate(c, lambdas, n_lambda, nullptr, nullptr, 0, c->max_family_size, 0, roots.data(), (int64_t)Fs, seed,
+                                    sim_counts.data(), nullptr, nullptr, nullptr);
+        if (rc != CAFE_B200_OK) return rc;
+        // 2. their likelihood at the root size they were generated from (compute_family_probabilities, :377-432; the reference
+        //    truncates each family's state space at its largest size + max(50, size/5), we keep the full space)
+        cafe_b200_tree t{n, c->parent.data(), c->branch_length.data(), c->leaf_col.data(), c->lambda_class.data()};
+        rc = cafe_b200_create(&t, sim_counts.data(), (int64_t)Fs, c->n_species, c->max_family_size, R, c->device, &sim);
+        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulated context: ") + g_create_error};
+        rc = cafe_b200_set_prior(sim, c->prior.data(), (int32_t)c->prior.size());
+        std::vector<double> vec(Fs * R);
+        if (rc == CAFE_B200_OK) rc = cafe_b200_root_vectors(sim, lambdas, n_lambda, 1.0, vec.data());
+        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulated families: ") + sim->err};
+        cafe_b200_destroy(sim);
+        sim = nullptr;
+        std::vector<std::vector<double>> cond(R, std::vector<double>(n_sims));
+        for (int r = 0; r < R; ++r) {
+            for (int i = 0; i < n_sims; ++i) cond[r][i] = vec[((size_t)r * n_sims + i) * R + r];   // index r <-> root size r+1
+            std::sort(cond[r].begin(), cond[r].end());
+        }
+        // 3. observed families: root vectors without the error model (compute_pvalues passes NULL, :549), then
+        //    find_best_pvalue (:513-526) over root sizes below rint(1.25 * largest count)
+        const bool had_em = c->have_em;
+        c->have_em = false;
+        vec.assign((size_t)c->F * R, 0.0);
+        rc = cafe_b200_root_vectors(c, lambdas, n_lambda, 1.0, vec.data());
+        c->have_em = had_em;
+        if (rc != CAFE_B200_OK) return rc;
+        for (int64_t f = 0; f < c->F; ++f) {
+            int mx = 0;
+            for (int j = 0; j < c->n_species; ++j) mx = std::max(mx, c->counts[(size_t)f * c->n_species + j]);
+            const int limit = std::min((int)std::rint(mx * 1.25), R);
+            double best = 0.0;
+            for (int j = 0; j < limit; ++j) {
+                const std::vector<double>& d = cond[j];
+                const double v = vec[(size_t)f * R + j];
+                size_t idx = d.size() - 1;
+                auto bound = std::upper_bound(d.begin(), d.end(), v);
+                if (bound != d.end()) idx = (size_t)(bound - d.begin());
+                best = std::max(best, (double)idx / (double)d.size());
+            }
+            pvalues[f] = best;
+        }
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) {
+        if (sim) cafe_b200_destroy(sim);
+        return fail(c, e);
+    }
 }
 
 }  // extern "C"

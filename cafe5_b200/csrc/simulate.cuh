@@ -3,7 +3,8 @@
 // its vectorised root distribution at index f), every other node draws its size from row `parent size` of its branch's transition
 // matrix restricted to sizes < max_sim (set_weighted_random_family_size, src/probability.cpp:449-476; matrix::select_random_y,
 // src/matrix_cache.cpp:60-66: a discrete distribution over the un-normalised row), a lost family stays lost, and a family that
-// does not exist at the root (src/gene_family.cpp:62-91) is redrawn, up to 50 times.  Under the gamma model each family first
+// does not exist at the root (src/gene_family.cpp:62-91) is redrawn, up to max_redraws times (50 in the reference's simulator, 0 for the conditional
+// distributions of the p-value path, whose create_family, src/probability.cpp:355-375, never redraws).  Under the gamma model each family first
 // picks one rate category with the category probabilities (gamma_model::get_simulation_lambda, src/gamma_core.cpp:91-95).
 // The random stream is counter-based (Philox4x32-10, keyed by the seed, counter = family index), so a run is reproducible for a
 // given seed whatever the launch geometry; it is NOT the reference's std::mt19937 stream: parity is distributional.
@@ -78,7 +79,7 @@ struct SimParams {
     unsigned long long* exhausted;
     int64_t F;
     uint64_t seed;
-    int32_t n_nodes, n_species, K, N, max_sim;
+    int32_t n_nodes, n_species, K, N, max_sim, max_attempts;
 };
 
 __global__ void __launch_bounds__(256)
@@ -100,7 +101,7 @@ simulate_kernel(const SimParams p)
     const int32_t* mat_of = p.mat_of + (size_t)cat * p.n_nodes;
     const int root = p.n_nodes - 1;
     bool ok = false;
-    for (int attempt = 0; attempt < 50 && !ok; ++attempt) {
+    for (int attempt = 0; attempt < p.max_attempts && !ok; ++attempt) {
         p.sizes[(size_t)root * p.F + f] = p.root_sizes[f];
         for (int i = root - 1; i >= 0; --i) {         // parents have larger indices: top-down
             const int ps = p.sizes[(size_t)p.parent[i] * p.F + f];

@@ -204,7 +204,14 @@ class Context:
     def stream(self):
         return self.lib.cafe_b200_stream(self.h)
 
-    def simulate(self, lambdas, root_sizes, multipliers=None, cat_probs=None, max_sim=120, seed=1, want_nodes=False):
+    def pvalues(self, lambdas, n_sims=1000, seed=1):
+        """Family-level Monte-Carlo p-values (cafe_b200_pvalues; compute_pvalues, src/probability.cpp:528-570)."""
+        lam = _lib.as_f64(lambdas)
+        out = np.zeros(self.F)
+        self._check(self.lib.cafe_b200_pvalues(self.h, _lib.dp(lam), len(lam), int(n_sims), int(seed), _lib.dp(out)), "pvalues")
+        return out
+
+    def simulate(self, lambdas, root_sizes, multipliers=None, cat_probs=None, max_sim=120, seed=1, want_nodes=False, max_redraws=50):
         """Simulate len(root_sizes) families on this context's tree (cafe_b200_simulate): dict(counts[F, n_species],
         categories[F], node_sizes[F, n_nodes] or None, n_not_at_root)."""
         lam = _lib.as_f64(lambdas)
@@ -217,7 +224,7 @@ class Context:
         cats = np.zeros(F, dtype=np.int32)
         nodes = np.zeros((F, self.n_nodes), dtype=np.int32) if want_nodes else None
         bad = C.c_int64()
-        self._check(self.lib.cafe_b200_simulate(self.h, _lib.dp(lam), len(lam), _lib.dp(mu), _lib.dp(cp), K, int(max_sim), _lib.ip(roots),
+        self._check(self.lib.cafe_b200_simulate(self.h, _lib.dp(lam), len(lam), _lib.dp(mu), _lib.dp(cp), K, int(max_sim), int(max_redraws), _lib.ip(roots),
                                                 F, int(seed), _lib.ip(counts), _lib.ip(nodes), _lib.ip(cats), C.byref(bad)), "simulate")
         return dict(counts=counts, categories=cats, node_sizes=nodes, n_not_at_root=bad.value)
 

@@ -140,15 +140,24 @@ typedef struct {
 int cafe_b200_fit(cafe_b200_ctx* ctx, const cafe_b200_fit_options* options, cafe_b200_fit_result* result);
 
 /* Simulator: simulator::create_trial (src/simulator.cpp:29-58) for n_families families on the context's
- * tree.  root_sizes[f] is the root size of family f (the reference reads its vectorised root distribution at index f); child sizes
+ * tree.  root_sizes[f] is the root size of family f (the reference reads its vectorised root distribution at index f); a family absent at the root is
+ * redrawn up to max_redraws times (the reference: 50); child sizes
  * are drawn from matrix rows restricted to sizes < max_sim (select_random_y, src/matrix_cache.cpp:60-66; the reference passes its
  * max_family_size, 120 by default); n_cat > 0: each family first picks a rate category with cat_probs (gamma_core.cpp:91-95).
  * counts[F x n_species] (the context's species columns); node_sizes[F x n_nodes] and categories[F] optional; n_not_at_root:
  * families still absent at the root after 50 redraws (kept, as the reference keeps them with a warning).  Counter-based RNG
  * (Philox4x32-10 keyed by seed, one stream per family): reproducible per seed, distributional parity with the reference. */
 int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
-                       int32_t n_cat, int32_t max_sim, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
+                       int32_t n_cat, int32_t max_sim, int32_t max_redraws, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
                        int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root);
+
+/* Family-level p-values: compute_pvalues (src/probability.cpp:528-570) with the model's own lambda.  For every
+ * root size 1..R, n_sims families are simulated from that root size (no error model, no redraws) and their likelihood AT that root
+ * size forms a sorted conditional distribution; a family's p-value is the largest, over root sizes below rint(1.25 * its largest
+ * count), of the fraction of that distribution not above the family's own root-vector entry (pvalue / find_best_pvalue, :501-526).
+ * The reference calls it with n_sims = 1000 (src/execute.cpp:171).  Monte-Carlo: agreement with the reference is statistical; the
+ * simulated families are pruned over the full state space where the reference truncates each at its largest size + max(50, size/5). */
+int cafe_b200_pvalues(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues);
 
 /* Test hooks ------------------------------------------------------------------------------- */
 

@@ -383,6 +383,14 @@ class RefLib:
                 raise RuntimeError("ref_optimize: " + self.ref.lib.ref_ctx_error(self.h).decode())
             return dict(values=vals[:nv.value].copy(), score=score.value, iterations=iters.value, attempts=attempts.value, seconds=secs.value)
 
+        def pvalues(self, lambdas, n_sims=1000, seed=1):
+            """compute_pvalues of the unmodified reference (src/probability.cpp:528-570), randomizer_engine seeded with `seed`."""
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            out = np.zeros(self.F)
+            self.ref.lib.ref_pvalues.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, C.c_uint, c_dp]
+            self.ref._check(self.ref.lib.ref_pvalues(self.h, _dp(lambdas), len(lambdas), int(n_sims), int(seed), _dp(out)))
+            return out
+
         def reconstruct_base(self, lambdas):
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
             st = np.zeros((self.F, self.n_nodes), dtype=np.int32)

@@ -310,6 +310,24 @@ int ref_eval_gamma(void* h, const double* lambdas, int n_lambda, const double* m
 }
 
 // Pupko reconstruction, base model.  states: F x n_nodes ints in reverse level order (leaves = observed).
+// Family-level p-values with the reference's own compute_pvalues (src/probability.cpp:528-570), called as estimator::execute does
+// (src/execute.cpp:164-171): matrices of size max(max_family_size, max_root) + 100 for the model's lambda.  randomizer_engine is
+// seeded here (the reference never seeds it).
+int ref_pvalues(void* h, const double* lambdas, int n_lambda, int n_sims, unsigned seed, double* out)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        randomizer_engine.seed(seed);
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+        cache.precalculate_matrices(get_lambda_values(lam.get()), c->tree->get_branch_lengths());
+        pvalue_parameters p = {c->tree.get(), lam.get(), c->max_family_size, c->max_root_family_size, cache};
+        auto pv = compute_pvalues(p, c->ud.gene_families, n_sims);
+        for (size_t i = 0; i < pv.size(); ++i) out[i] = pv[i];
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
 int ref_reconstruct_base(void* h, const double* lambdas, int n_lambda, int* states)
 {
     auto c = (ref_ctx*)h;
