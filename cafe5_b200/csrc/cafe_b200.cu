@@ -304,7 +304,7 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
                 if (tiles >= 2 * (int64_t)c->n_sms * ctas) break;
                 tnw >>= 1;
             }
-            if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);   // experiment knob
+            if (const char* e = std::getenv("CAFE_B200_TNW")) { const int v = std::atoi(e); if (v >= 1 && v <= 4) tnw = v; }   // experiment knob
             const size_t fixed = resident_fixed_bytes(tnw, wn, c->N), stage = resident_stage_bytes(c->TM, bk);
             if (fixed + 2 * stage > avail) continue;
             int stages = (int)std::min<size_t>((avail - fixed) / stage, 8);
@@ -326,7 +326,7 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
         if (tiles >= 2 * (int64_t)c->n_sms) break;
         tnw >>= 1;
     }
-    if (const char* e = std::getenv("CAFE_B200_TNW")) tnw = std::atoi(e);
+    if (const char* e = std::getenv("CAFE_B200_TNW")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) tnw = v; }
     c->TNW = tnw;
     c->WN = 4;
     const int bn = 32 * tnw, bm = 16 * c->TM;
