@@ -49,6 +49,13 @@ t = time.time(); r = pctx.fit(seed=10, n_cat=0); r["wall_s"] = time.time() - t; 
 out["config3_errormodel_two_lambdas_product"] = r
 print("config3_errormodel_two_lambdas product driver", json.dumps(r), flush=True)
 pctx.close()
+if not os.environ.get("SKIP_CPU"):   # the reference's optimizer on its CPU models, same seed (~3 minutes on 16 threads)
+    rctx3 = ref.ctx(str(g["newick"]), species, counts, mfs, mrs, fam.uniform_prior(mrs), lambda_newick=str(g["lambda_newick"]),
+                    em=(g["em_probs"], int(g["em_maxcnt"])))
+    t = time.time(); r = rctx3.optimize("cpu", seed=10, n_cat=0); r["wall_s"] = time.time() - t; r["values"] = [float(v) for v in r["values"]]
+    out["config3_errormodel_two_lambdas_cpu"] = r
+    print("config3_errormodel_two_lambdas reference cpu", json.dumps(r), flush=True)
+    rctx3.close()
 h = np.load(os.path.join(ROOT, "tests", "golden", "hymenoptera.npz"))
 treeh = FlatTree(str(h["newick"]), species=[str(x) for x in h["species"]])
 hm, hr = int(h["max_family_size"]), int(h["max_root_family_size"])
