@@ -1,0 +1,82 @@
+"""ctypes view of the library's C++ readers / writers of the reference's on-disk formats (cafe5_b200/host/io.hpp).
+Host-only: works without a GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class IoError(RuntimeError):
+    pass
+
+
+def _check(L, rc):
+    if rc:
+        raise IoError(L.cafe_b200_io_last_error().decode())
+
+
+def parse_tree(newick, lambda_newick=None, capacity=8192):
+    """dict(parent, branch_length, is_leaf, lambda_class, n_lambda, names): nodes in the reference's reverse level order."""
+    L = _lib.load()
+    n, nl = C.c_int32(), C.c_int32()
+    parent = np.zeros(capacity, dtype=np.int32)
+    bl = np.zeros(capacity)
+    leaf = np.zeros(capacity, dtype=np.int32)
+    cls = np.zeros(capacity, dtype=np.int32)
+    buf = C.create_string_buffer(1 << 20)
+    _check(L, L.cafe_b200_io_parse_tree(newick.encode(), (lambda_newick or "").encode(), capacity, C.byref(n), _lib.ip(parent), _lib.dp(bl),
+                                       _lib.ip(leaf), _lib.ip(cls), C.byref(nl), buf, len(buf)))
+    k = n.value
+    return dict(parent=parent[:k].copy(), branch_length=bl[:k].copy(), is_leaf=leaf[:k].astype(bool), lambda_class=cls[:k].copy(),
+                n_lambda=nl.value, names=buf.value.decode().split("\t"))
+
+
+def read_gene_families(path):
+    """(species, ids, counts[F, n_species] int32)."""
+    L = _lib.load()
+    nf, ns = C.c_int64(), C.c_int32()
+    _check(L, L.cafe_b200_io_read_families(str(path).encode(), C.byref(nf), C.byref(ns), None, 0, None, 0, None, 0))
+    counts = np.zeros((nf.value, ns.value), dtype=np.int32)
+    sp = C.create_string_buffer(1 << 20)
+    ids = C.create_string_buffer(max(1 << 20, 64 * nf.value))
+    _check(L, L.cafe_b200_io_read_families(str(path).encode(), C.byref(nf), C.byref(ns), _lib.ip(counts), counts.size, sp, len(sp), ids, len(ids)))
+    return sp.value.decode().split("\t"), ids.value.decode().split("\t"), counts
+
+
+def read_error_model(path, rows_cap=100000):
+    L = _lib.load()
+    probs = np.zeros((rows_cap, 3))
+    rows, mx = C.c_int32(), C.c_int32()
+    _check(L, L.cafe_b200_io_read_error_model(str(path).encode(), _lib.dp(probs), rows_cap, C.byref(rows), C.byref(mx)))
+    return probs[:rows.value].copy(), mx.value
+
+
+def derive_sizes(counts):
+    L = _lib.load()
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    a, b = C.c_int32(), C.c_int32()
+    _check(L, L.cafe_b200_io_derive_sizes(_lib.ip(c), c.size, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def format_results(model_name, neg_lnl, lambdas, longest_branch, attempts, rejects, epsilon=float("nan"), alpha=float("nan")):
+    L = _lib.load()
+    lam = _lib.as_f64(lambdas)
+    buf = C.create_string_buffer(1 << 16)
+    _check(L, L.cafe_b200_io_format_results(model_name.encode(), float(neg_lnl), _lib.dp(lam), len(lam), float(epsilon), float(longest_branch),
+                                           int(attempts), int(rejects), float(alpha), buf, len(buf)))
+    return buf.value.decode()
+
+
+def format_family_likelihoods(ids, what, family_values=None, multipliers=None, cat_lk=None, posterior=None, significant=None):
+    """what: 'base' | 'gamma' | 'categories'."""
+    L = _lib.load()
+    K = 0 if multipliers is None else len(multipliers)
+    arr = lambda a: None if a is None else _lib.as_f64(a)   # noqa: E731
+    mu, cl, fv, po = arr(multipliers), arr(cat_lk), arr(family_values), arr(posterior)
+    sg = None if significant is None else np.ascontiguousarray(significant, dtype=np.uint8)
+    buf = C.create_string_buffer(256 * max(1, len(ids)) * max(1, K) + 4096)
+    _check(L, L.cafe_b200_io_format_family_likelihoods("\t".join(ids).encode(), len(ids), K, _lib.dp(mu), _lib.dp(cl), _lib.dp(fv), _lib.dp(po),
+                                                      _lib.up(sg), {"base": 0, "gamma": 1, "categories": 2}[what], buf, len(buf)))
+    return buf.value.decode()

@@ -159,6 +159,38 @@ int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lamb
  * simulated families are pruned over the full state space where the reference truncates each at its largest size + max(50, size/5). */
 int cafe_b200_pvalues(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues);
 
+/* On-disk formats: cafe5_b200/host/io.hpp through a C interface.  Host-only (no GPU needed).  Lists of
+ * strings come back tab-separated in caller-owned buffers. -------------------------------------------------------------------- */
+
+const char* cafe_b200_io_last_error(void);
+
+/* Newick species tree (+ optional lambda tree) -> the flattened arrays cafe_b200_create takes, nodes in the reference's reverse
+ * level order (src/clade.cpp:69-100, 293-419; interior nodes named as src/clade.cpp:161-173; lambda classes src/clade.cpp:194-204). */
+int cafe_b200_io_parse_tree(const char* newick, const char* lambda_newick, int32_t capacity, int32_t* n_nodes, int32_t* parent,
+                            double* branch_length, int32_t* is_leaf, int32_t* lambda_class, int32_t* n_lambda, char* names, int64_t names_cap);
+
+/* Gene-family table, CAFE or CAFExp header style (src/io.cpp:134-217): counts[n_families x n_species]. */
+int cafe_b200_io_read_families(const char* path, int64_t* n_families, int32_t* n_species, int32_t* counts, int64_t counts_cap,
+                               char* species, int64_t species_cap, char* ids, int64_t ids_cap);
+
+/* Error-model file (src/io.cpp:228-274, src/error_model.cpp:31-50): probs[rows x 3]. */
+int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_cap, int32_t* rows, int32_t* max_count);
+
+/* max_family_size / max_root_family_size from the count table (src/user_data.cpp:40-48, floors src/user_data.h:26-27). */
+int cafe_b200_io_derive_sizes(const int32_t* counts, int64_t n, int32_t* max_family_size, int32_t* max_root_family_size);
+
+/* <Model>_results.txt (model::write_vital_statistics, src/core.cpp:97-112; gamma: src/gamma_core.cpp:46-50); epsilon / alpha = NaN
+ * when the model has none. */
+int cafe_b200_io_format_results(const char* model_name, double neg_lnl, const double* lambdas, int32_t n_lambda, double epsilon,
+                                double longest_branch, int32_t attempts, int32_t rejects, double alpha, char* out, int64_t out_cap);
+
+/* what = 0: Base_family_likelihoods.txt (src/base_model.cpp:102-109; family_values = family lnL); 1: Gamma_family_likelihoods.txt
+ * (src/gamma_core.cpp:52-58, src/core.cpp:53-58; family_values = family likelihood); 2: Gamma_category_likelihoods.txt
+ * (src/gamma_core.cpp:359-374). */
+int cafe_b200_io_format_family_likelihoods(const char* ids_tabbed, int64_t n_families, int32_t n_cat, const double* multipliers,
+                                           const double* cat_lk, const double* family_values, const double* posterior,
+                                           const uint8_t* significant, int32_t what, char* out, int64_t out_cap);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

@@ -288,6 +288,26 @@ class RefLib:
     def max_threads(self):
         return self.lib.ref_max_threads()
 
+    def read_families(self, path, newick, cap=4000000):
+        """The reference's read_gene_families against `newick`: (ids, counts[F, n_leaves]) with leaves in reverse level order."""
+        n = C.c_long()
+        counts = np.zeros(cap, dtype=np.int32)
+        ids = C.create_string_buffer(1 << 22)
+        self.lib.ref_read_families.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_long), c_ip, C.c_long, C.c_char_p, C.c_long]
+        self._check(self.lib.ref_read_families(str(path).encode(), newick.encode(), C.byref(n), _ip(counts), cap, ids, len(ids)))
+        F = n.value
+        ids_list = ids.value.decode().split("\t")
+        # the number of leaves is whatever makes the flat buffer F rows long: count the tree's leaves through flatten()
+        leaves = int(np.sum(self.flatten(newick)[2]))
+        return ids_list, counts[:F * leaves].reshape(F, leaves).copy()
+
+    def read_error_model(self, path, rows_cap=100000):
+        probs = np.zeros((rows_cap, 3))
+        rows, mx = C.c_int(), C.c_int()
+        self.lib.ref_read_error_model.argtypes = [C.c_char_p, c_dp, C.c_int, c_ip, c_ip]
+        self._check(self.lib.ref_read_error_model(str(path).encode(), _dp(probs), rows_cap, C.byref(rows), C.byref(mx)))
+        return probs[:rows.value].copy(), mx.value
+
     def fminsearch(self, fn, x0, max_iterations=300):
         """The reference's fminsearch_min (src/optimizer.cpp:287-322) over a Python objective."""
         CB = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
@@ -382,6 +402,19 @@ class RefLib:
             if rc:
                 raise RuntimeError("ref_optimize: " + self.ref.lib.ref_ctx_error(self.h).decode())
             return dict(values=vals[:nv.value].copy(), score=score.value, iterations=iters.value, attempts=attempts.value, seconds=secs.value)
+
+        def write_outputs(self, lambdas, multipliers=None, cat_probs=None, alpha=0.0):
+            """(family_likelihoods text, results text, category_likelihoods text) exactly as the reference writes them."""
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            K = 0 if multipliers is None else len(multipliers)
+            mu = None if K == 0 else np.ascontiguousarray(multipliers, dtype=np.float64)
+            cp = None if K == 0 else np.ascontiguousarray(cat_probs, dtype=np.float64)
+            bufs = [C.create_string_buffer(1 << 24), C.create_string_buffer(1 << 16), C.create_string_buffer(1 << 24)]
+            self.ref.lib.ref_write_outputs.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, C.c_double,
+                                                       C.c_char_p, C.c_long, C.c_char_p, C.c_long, C.c_char_p, C.c_long]
+            self.ref._check(self.ref.lib.ref_write_outputs(self.h, _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K, float(alpha),
+                                                           bufs[0], len(bufs[0]), bufs[1], len(bufs[1]), bufs[2], len(bufs[2])))
+            return tuple(b.value.decode() for b in bufs)
 
         def pvalues(self, lambdas, n_sims=1000, seed=1):
             """compute_pvalues of the unmodified reference (src/probability.cpp:528-570), randomizer_engine seeded with `seed`."""

@@ -17,6 +17,7 @@
 // gamma_model::_category_likelihoods) can be read without modifying the reference.
 // No reference source is copied into this repository.
 #include <cstring>
+#include <fstream>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -309,7 +310,6 @@ int ref_eval_gamma(void* h, const double* lambdas, int n_lambda, const double* m
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
-// Pupko reconstruction, base model.  states: F x n_nodes ints in reverse level order (leaves = observed).
 // Family-level p-values with the reference's own compute_pvalues (src/probability.cpp:528-570), called as estimator::execute does
 // (src/execute.cpp:164-171): matrices of size max(max_family_size, max_root) + 100 for the model's lambda.  randomizer_engine is
 // seeded here (the reference never seeds it).
@@ -328,6 +328,89 @@ int ref_pvalues(void* h, const double* lambdas, int n_lambda, int n_sims, unsign
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// ---- the reference's own readers and writers (pins cafe5_b200/host/io.hpp) -----------------------------------------------------
+static int put_text(const std::string& s, char* buf, long cap)
+{
+    if ((long)s.size() + 1 > cap) { g_err = "buffer too small"; return 1; }
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+
+// read_gene_families (src/io.cpp:134-217) against the tree `newick`: counts F x n_leaves in the tree's reverse-level leaf order
+int ref_read_families(const char* path, const char* newick, long* n_families, int* counts, long counts_cap, char* ids, long ids_cap)
+{
+    try {
+        std::unique_ptr<clade> tree(parse_newick(newick));
+        std::ifstream in(path);
+        std::vector<gene_family> fams;
+        read_gene_families(in, tree.get(), fams);
+        std::vector<std::string> leaves;
+        for (auto it = tree->reverse_level_begin(); it != tree->reverse_level_end(); ++it)
+            if ((*it)->is_leaf()) leaves.push_back((*it)->get_taxon_name());
+        *n_families = (long)fams.size();
+        if ((long)(fams.size() * leaves.size()) > counts_cap) { g_err = "counts buffer too small"; return 1; }
+        std::string all;
+        for (size_t f = 0; f < fams.size(); ++f) {
+            for (size_t j = 0; j < leaves.size(); ++j) counts[f * leaves.size() + j] = fams[f].get_species_size(leaves[j]);
+            if (f) all += '\t';
+            all += fams[f].id();
+        }
+        return put_text(all, ids, ids_cap);
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// read_error_model_file (src/io.cpp:228-274): every row the model holds, as get_probs returns them
+int ref_read_error_model(const char* path, double* probs, int rows_cap, int* rows, int* max_count)
+{
+    try {
+        std::ifstream in(path);
+        error_model em;
+        read_error_model_file(in, &em);
+        const int n = (int)em.get_max_family_size();          // number of rows (error_model.h:55-57)
+        *max_count = (int)em._max_family_size;                // the "maxcnt" line
+        *rows = n;
+        if (n > rows_cap) { g_err = "probs buffer too small"; return 1; }
+        for (int i = 0; i < n; ++i) {
+            auto r = em.get_probs(i);
+            for (int d = 0; d < 3; ++d) probs[i * 3 + d] = r[d];
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// The text the reference writes for one evaluated model: *_family_likelihoods.txt (base_model.cpp:102-109 / gamma_core.cpp:52-58),
+// *_results.txt (write_vital_statistics, core.cpp:97-112, gamma_core.cpp:46-50) and, for the gamma model,
+// Gamma_category_likelihoods.txt (gamma_core.cpp:359-374).  K == 0: base model.
+int ref_write_outputs(void* h, const double* lambdas, int n_lambda, const double* multipliers, const double* cat_probs, int K, double alpha,
+                      char* fam, long fam_cap, char* res, long res_cap, char* cat, long cat_cap)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        std::ostringstream a, b, d;
+        if (K == 0) {
+            base_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, c->em.get());
+            const double score = m.infer_family_likelihoods(c->ud.prior, lam.get());
+            m.write_family_likelihoods(a);
+            m.write_vital_statistics(b, score);
+        } else {
+            gamma_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size,
+                          std::vector<double>(cat_probs, cat_probs + K), std::vector<double>(multipliers, multipliers + K), c->em.get());
+            m._alpha = alpha;
+            const double score = m.infer_family_likelihoods(c->ud.prior, lam.get());
+            m.write_family_likelihoods(a);
+            m.write_vital_statistics(b, score);
+            matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+            std::unique_ptr<reconstruction> rec(m.reconstruct_ancestral_states(c->ud, c->ui, &cache));
+            cladevector order;
+            dynamic_cast<gamma_model_reconstruction*>(rec.get())->print_category_likelihoods(d, order);
+        }
+        if (put_text(a.str(), fam, fam_cap) || put_text(b.str(), res, res_cap) || put_text(d.str(), cat, cat_cap)) return 1;
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Pupko reconstruction, base model.  states: F x n_nodes ints in reverse level order (leaves = observed).
 int ref_reconstruct_base(void* h, const double* lambdas, int n_lambda, int* states)
 {
     auto c = (ref_ctx*)h;

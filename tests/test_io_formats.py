@@ -1,0 +1,146 @@
+"""the library's C++ readers and writers of the reference's on-disk formats (cafe5_b200/host/io.hpp, reached through
+the C ABI) against the reference's own parsers and writers (oracle/_ref, compiled from the unmodified sources) and against the files
+the reference ships.  Host-only: runs without a GPU."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from cafe5_b200 import families as fam
+from cafe5_b200 import io_cpp
+from cafe5_b200.gamma import get_gamma
+from cafe5_b200.tree import FlatTree
+
+REF = os.environ.get("CAFE_REF_DIR", "/root/reference")
+needs_files = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "examples")), reason="reference example files absent")
+
+TREES = [
+    "((A:1,B:1):1,(C:1,D:1):1);",
+    "(((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)",
+    "((E:0.36,D:0.30)H:1.00,(C:0.85,(A:0.59,B:0.35)F:0.42)G:0.45)I;",           # interior labels are kept
+    "((A:1,B:1,C:2.5):4,(D:3,(E:1,F:1):2):3.5)",                                   # multifurcation
+    "A:1,B:3",                                                                    # no outer parentheses
+]
+
+
+@pytest.mark.parametrize("newick", TREES)
+def test_cpp_tree_parser_matches_reference(ref, newick):
+    parent, bl, is_leaf, _, names = ref.flatten(newick)
+    t = io_cpp.parse_tree(newick)
+    assert np.array_equal(t["parent"], parent) and np.array_equal(t["branch_length"], bl)
+    assert np.array_equal(t["is_leaf"], is_leaf.astype(bool)) and t["names"] == names
+    py = FlatTree(newick)
+    assert np.array_equal(t["parent"], py.parent) and t["names"] == py.names
+
+
+def test_cpp_lambda_tree_classes_match_reference(ref):
+    newick = "(((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)"
+    lam = "(((chimp:2,human:2):2,(mouse:1,rat:1):1):1,dog:1)"
+    _, _, _, cls, _ = ref.flatten(newick, lam)
+    t = io_cpp.parse_tree(newick, lam)
+    assert np.array_equal(t["lambda_class"], cls) and t["n_lambda"] == 2
+    with pytest.raises(io_cpp.IoError):
+        io_cpp.parse_tree(newick, "((chimp:2,human:2):2,dog:1)")               # structure mismatch (clade.cpp:247-262)
+    with pytest.raises(io_cpp.IoError):
+        io_cpp.parse_tree("((A:1,B:0):1,C:2)")                                   # non-positive branch length (clade.cpp:411-414)
+
+
+@needs_files
+def test_cpp_family_reader_on_the_reference_examples(ref):
+    newick = open(os.path.join(REF, "examples", "mammals_tree.txt")).readline().strip()
+    path = os.path.join(REF, "examples", "mammal_gene_families.txt")
+    species, ids, counts = io_cpp.read_gene_families(path)
+    rids, rcounts = ref.read_families(path, newick)
+    t = io_cpp.parse_tree(newick)
+    leaves = [n for n, leaf in zip(t["names"], t["is_leaf"]) if leaf]
+    col = {s.lower(): j for j, s in enumerate(species)}
+    assert ids == rids
+    assert np.array_equal(counts[:, [col[n.lower()] for n in leaves]], rcounts)
+    assert io_cpp.derive_sizes(counts) == fam.derive_sizes(counts) == (170, 150)
+
+
+def test_cpp_family_reader_both_header_styles(tmp_path, ref):
+    newick = "((A:1,B:1):1,(C:1,D:1):1)"
+    cafe = tmp_path / "cafe.txt"
+    cafe.write_text("Desc\tFamily ID\tA\tB\tC\tD\n\n(null)\tfam1\t5\t10\t2\t6\n(null)\tfam2\t5\t10abc\t-2\t6\r\n")
+    cafexp = tmp_path / "cafexp.txt"
+    cafexp.write_text("#A\n#B\n#C\n#D\n5\t10\t2\t6\tfam1\n1\t0\t3\t7\tfam2\n")
+    for path in (cafe, cafexp):
+        species, ids, counts = io_cpp.read_gene_families(path)
+        sp2, ids2, c2 = fam.read_gene_families(path)
+        assert species == sp2 == ["A", "B", "C", "D"] and ids == ids2 and np.array_equal(counts, c2)
+        rids, rcounts = ref.read_families(path, newick)
+        # the reference's tree order of the leaves of this newick is D C B A (reverse level order)
+        t = io_cpp.parse_tree(newick)
+        leaves = [n for n, leaf in zip(t["names"], t["is_leaf"]) if leaf]
+        assert ids == rids and np.array_equal(counts[:, [species.index(n) for n in leaves]], rcounts)
+    with pytest.raises(io_cpp.IoError):
+        empty = tmp_path / "empty.txt"
+        empty.write_text("Desc\tFamily ID\tA\tB\n")
+        io_cpp.read_gene_families(empty)
+
+
+@needs_files
+def test_cpp_error_model_reader_matches_reference(ref, tmp_path):
+    path = os.path.join(REF, "examples", "errormodel_0.1.txt")
+    probs, mx = io_cpp.read_error_model(path)
+    rprobs, rmx = ref.read_error_model(path)
+    pprobs, pmx = fam.read_error_model(path)
+    assert mx == rmx == pmx
+    assert np.array_equal(probs, rprobs) and np.array_equal(probs, pprobs)
+    sparse = tmp_path / "em.txt"
+    sparse.write_text("maxcnt:10\ncntdiff -1 0 1\n0 0.0 0.8 0.2\n1 0.2 0.6 0.2\n5 0.3 0.5 0.2\n")
+    probs, mx = io_cpp.read_error_model(sparse)
+    rprobs, _ = ref.read_error_model(sparse)
+    assert mx == 10 and np.array_equal(probs, rprobs) and np.array_equal(probs[2], probs[1])   # missing sizes inherit the previous row
+    bad = tmp_path / "bad.txt"
+    bad.write_text("maxcnt:10\ncntdiff -1 0 1\n0 0.2 0.6 0.2\n")
+    with pytest.raises(io_cpp.IoError):
+        io_cpp.read_error_model(bad)
+
+
+def _small_problem():
+    newick = "(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25)"
+    rng = np.random.default_rng(21)
+    base = rng.integers(1, 25, size=12)
+    counts = np.clip(base[:, None] + rng.integers(-3, 4, size=(12, 7)), 0, 40).astype(np.int32)
+    return newick, counts
+
+
+def test_cpp_writers_reproduce_the_reference_text(ref, oracle):
+    """Feed the writers the C oracle's numbers (equal to the reference's to ~1e-14) and compare with what the reference's own
+    write_family_likelihoods / write_vital_statistics / print_category_likelihoods print for the same model."""
+    newick, counts = _small_problem()
+    tree = FlatTree(newick)
+    mfs, mrs = 60, 45
+    prior = fam.uniform_prior(mrs)
+    ids = [str(i) for i in range(counts.shape[0])]
+    rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, prior)
+    lam = [0.0123456789]
+    # base model
+    fam_txt, res_txt, _ = rctx.write_outputs(lam)
+    want = oracle.eval_base(tree, counts, mfs, mrs, prior, lam)
+    assert io_cpp.format_family_likelihoods(ids, "base", family_values=want["family_lnl"]) == fam_txt
+    longest = float(tree.branch_length.max())
+    assert io_cpp.format_results("Base", want["neg_lnl"], lam, longest, 1, 0) == res_txt
+    # gamma model
+    alpha = 0.7
+    cp, mu = get_gamma(3, alpha)
+    fam_txt, res_txt, cat_txt = rctx.write_outputs(lam, mu, cp, alpha=alpha)
+    og = oracle.eval_gamma(tree, counts, mfs, mrs, prior, lam, mu, cp, alpha=alpha)
+    assert io_cpp.format_family_likelihoods(ids, "gamma", family_values=og["family_lk"], multipliers=mu, cat_lk=og["cat_lk"],
+                                            posterior=og["posterior"], significant=og["significant"]) == fam_txt
+    assert io_cpp.format_results("Gamma", og["neg_lnl"], lam, longest, 1, 0, alpha=alpha) == res_txt
+    assert io_cpp.format_family_likelihoods(ids, "categories", multipliers=mu, cat_lk=og["cat_lk"]) == cat_txt
+    rctx.close()
+
+
+def test_cpp_results_writer_with_two_lambdas_and_epsilon():
+    txt = io_cpp.format_results("Base", 154503.34090635672, [0.0008193138839916892, 0.0096118070615455], 93.0, 141, 7, epsilon=0.05)
+    assert txt.splitlines() == ["Model Base Final Likelihood (-lnL): 154503",
+                                "Lambda: 0.00081931388399169, 0.0096118070615455",
+                                "Epsilon: 0.05",
+                                "Maximum possible lambda for this topology: 0.0107527",
+                                "141 values were attempted (5% rejected)"]
+    assert not math.isnan(float(txt.split()[5]))
