@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <functional>
 #include <iomanip>
 #include <istream>
 #include <map>
@@ -375,6 +376,122 @@ inline void write_category_likelihoods(std::ostream& ost, const std::vector<std:
         ost << ids[f] << '\t';
         for (int k = 0; k < K; ++k) ost << cat_lk[f * K + k] << "\t";
         ost << std::endl;
+    }
+}
+
+// ---- reconstruction tables (reconstruction::write_results, src/gene_family_reconstructor.cpp:352-379) ------------------------------
+// The reference labels nodes with the numbering R's ape package gives the tree (get_ape_order, src/newick_ape_loader.cpp:213-242):
+// tips 1..n in their left-to-right order in the newick text, the root n+1, the other interior nodes n+2.. in preorder.
+// Returns id[node] for the Tree's node order; the children of a node, left to right, are its children by DEcreasing index.
+inline std::vector<int> ape_ids(const Tree& t)
+{
+    const int n = t.n_nodes();
+    std::vector<std::vector<int>> kids(n);
+    for (int i = n - 1; i >= 0; --i) if (t.parent[i] >= 0) kids[t.parent[i]].push_back(i);
+    int n_tips = 0;
+    for (int i = 0; i < n; ++i) n_tips += t.is_leaf[i];
+    std::vector<int> id(n, 0), stack{n - 1};
+    int next_tip = 1, next_inner = n_tips + 1;
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        id[v] = t.is_leaf[v] ? next_tip++ : next_inner++;
+        for (auto it = kids[v].rbegin(); it != kids[v].rend(); ++it) stack.push_back(*it);   // leftmost child on top
+    }
+    return id;
+}
+
+// clade_index_or_name (src/clade.cpp:225-234)
+inline std::string node_label(const Tree& t, const std::vector<int>& ape, int node)
+{
+    return (t.is_leaf[node] ? t.name[node] : std::string()) + "<" + std::to_string(ape[node]) + ">";
+}
+
+inline std::vector<int> nodes_in_ape_order(const std::vector<int>& ape)
+{
+    std::vector<int> order(ape.size());
+    for (size_t i = 0; i < ape.size(); ++i) order[ape[i] - 1] = (int)i;
+    return order;
+}
+
+// <Model>_count.tab / <Model>_change.tab (print_node_counts :341-350, print_node_change :203-210, print_family_clade_table :270-277).
+// states[F x n_nodes]: reconstructed counts in the Tree's node order, leaves = observed counts.
+inline void write_node_table(std::ostream& ost, const Tree& t, const std::vector<std::string>& ids, const int32_t* states, bool change)
+{
+    const std::vector<int> ape = ape_ids(t), order = nodes_in_ape_order(ape);
+    const int n = t.n_nodes();
+    ost << "FamilyID";
+    for (int v : order) ost << "\t" << node_label(t, ape, v);
+    ost << std::endl;
+    for (size_t f = 0; f < ids.size(); ++f) {
+        ost << ids[f];
+        for (int v : order) {
+            const int here = states[f * n + v];
+            ost << "\t" << (change ? (t.parent[v] < 0 ? 0 : here - states[f * n + t.parent[v]]) : here);
+        }
+        ost << std::endl;
+    }
+}
+
+// <Model>_asr.tre (print_reconstructed_states :302-339, newick_node :192-201, clade::write_newick src/clade.cpp:206-223); no branch
+// probabilities (no node is starred); the gamma model appends its multipliers (write_nexus_extensions, src/gamma_core.cpp:341-349)
+inline void write_asr_trees(std::ostream& ost, const Tree& t, const std::vector<std::string>& ids, const int32_t* states,
+                            const std::vector<double>& gamma_multipliers = std::vector<double>())
+{
+    const std::vector<int> ape = ape_ids(t);
+    const int n = t.n_nodes();
+    std::vector<std::vector<int>> kids(n);
+    for (int i = n - 1; i >= 0; --i) if (t.parent[i] >= 0) kids[t.parent[i]].push_back(i);
+    ost << "#nexus\nBEGIN TREES;\n";
+    for (size_t f = 0; f < ids.size(); ++f) {
+        const int32_t* st = states + f * n;
+        std::function<void(int)> emit = [&](int v) {
+            if (!kids[v].empty()) {
+                ost << '(';
+                for (size_t i = 0; i < kids[v].size(); ++i) { if (i) ost << ','; emit(kids[v][i]); }
+                ost << ')';
+            }
+            std::ostringstream node;
+            node << node_label(t, ape, v) << "_" << st[v];
+            if (t.parent[v] >= 0) node << ':' << t.branch_length[v];
+            ost << node.str();
+        };
+        ost << "  TREE " << ids[f] << " = ";
+        emit(n - 1);
+        ost << ';' << std::endl;
+    }
+    ost << "\nEND;\n";
+    if (!gamma_multipliers.empty()) {
+        ost << "\nBEGIN LAMBDA_MULTIPLIERS;\n";
+        for (double m : gamma_multipliers) ost << "  " << m << ";\n";
+        ost << "END;\n\n";
+    }
+}
+
+// <Model>_family_results.txt (print_increases_decreases_by_family :213-232)
+inline void write_family_results(std::ostream& ost, const std::vector<std::string>& ids, const double* pvalues, double threshold)
+{
+    if (ids.empty()) { ost << "No increases or decreases recorded\n"; return; }
+    ost << "#FamilyID\tpvalue\tSignificant at " << threshold << "\n";
+    for (size_t f = 0; f < ids.size(); ++f) ost << ids[f] << '\t' << pvalues[f] << '\t' << (pvalues[f] < threshold ? 'y' : 'n') << std::endl;
+}
+
+// <Model>_clade_results.txt (print_increases_decreases_by_clade :234-256): nodes that changed in at least one family.  The reference
+// lists them in the order of their addresses in memory; here they come in ape order (compare as a set of lines).
+inline void write_clade_results(std::ostream& ost, const Tree& t, size_t n_families, const int32_t* states)
+{
+    const std::vector<int> ape = ape_ids(t), order = nodes_in_ape_order(ape);
+    const int n = t.n_nodes();
+    ost << "#Taxon_ID\tIncrease\tDecrease\n";
+    for (int v : order) {
+        if (t.parent[v] < 0) continue;
+        int up = 0, down = 0;
+        for (size_t f = 0; f < n_families; ++f) {
+            const int d = states[f * n + v] - states[f * n + t.parent[v]];
+            up += d > 0;
+            down += d < 0;
+        }
+        if (up || down) ost << node_label(t, ape, v) << "\t" << up << "\t" << down << std::endl;
     }
 }
 

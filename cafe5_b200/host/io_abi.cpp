@@ -128,4 +128,24 @@ int cafe_b200_io_format_family_likelihoods(const char* ids_tabbed, int64_t n_fam
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
+int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbed, int64_t n_families, const int32_t* states,
+                                       const double* pvalues, double pvalue_threshold, const double* gamma_multipliers, int32_t n_cat,
+                                       int32_t what, char* out, int64_t out_cap)
+{
+    try {
+        if (!newick || !states) throw std::runtime_error("null argument");
+        const cafe_b200_host::Tree t = cafe_b200_host::parse_newick(newick);
+        const std::vector<std::string> ids = ids_from(ids_tabbed, n_families);
+        std::ostringstream ost;
+        switch (what) {
+        case 0: cafe_b200_host::write_node_table(ost, t, ids, states, false); break;
+        case 1: cafe_b200_host::write_node_table(ost, t, ids, states, true); break;
+        case 2: cafe_b200_host::write_asr_trees(ost, t, ids, states, std::vector<double>(gamma_multipliers, gamma_multipliers + (gamma_multipliers ? n_cat : 0))); break;
+        case 3: if (!pvalues) throw std::runtime_error("p-values required"); cafe_b200_host::write_family_results(ost, ids, pvalues, pvalue_threshold); break;
+        default: cafe_b200_host::write_clade_results(ost, t, (size_t)n_families, states); break;
+        }
+        return put(ost.str(), out, out_cap);
+    } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
+}
+
 }  // extern "C"

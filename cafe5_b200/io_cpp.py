@@ -80,3 +80,16 @@ def format_family_likelihoods(ids, what, family_values=None, multipliers=None, c
     _check(L, L.cafe_b200_io_format_family_likelihoods("\t".join(ids).encode(), len(ids), K, _lib.dp(mu), _lib.dp(cl), _lib.dp(fv), _lib.dp(po),
                                                       _lib.up(sg), {"base": 0, "gamma": 1, "categories": 2}[what], buf, len(buf)))
     return buf.value.decode()
+
+
+def format_reconstruction(newick, ids, states, what, pvalues=None, threshold=0.05, gamma_multipliers=None):
+    """what: 'count' | 'change' | 'asr' | 'family_results' | 'clade_results'; states[F, n_nodes] as cafe_b200_reconstruct returns them."""
+    L = _lib.load()
+    st = np.ascontiguousarray(states, dtype=np.int32)
+    pv = None if pvalues is None else _lib.as_f64(pvalues)
+    mu = None if gamma_multipliers is None else _lib.as_f64(gamma_multipliers)
+    buf = C.create_string_buffer(64 * st.size + (1 << 16))
+    _check(L, L.cafe_b200_io_format_reconstruction(newick.encode(), "\t".join(ids).encode(), len(ids), _lib.ip(st), _lib.dp(pv), float(threshold),
+                                                  _lib.dp(mu), 0 if mu is None else len(mu),
+                                                  {"count": 0, "change": 1, "asr": 2, "family_results": 3, "clade_results": 4}[what], buf, len(buf)))
+    return buf.value.decode()

@@ -191,6 +191,15 @@ int cafe_b200_io_format_family_likelihoods(const char* ids_tabbed, int64_t n_fam
                                            const double* cat_lk, const double* family_values, const double* posterior,
                                            const uint8_t* significant, int32_t what, char* out, int64_t out_cap);
 
+/* Reconstruction tables (reconstruction::write_results, src/gene_family_reconstructor.cpp:352-379) from the states cafe_b200_reconstruct
+ * returns (states[F x n_nodes], nodes in the order cafe_b200_io_parse_tree gives for `newick`), nodes labelled with the reference's
+ * ape numbering.  what = 0: <Model>_count.tab; 1: <Model>_change.tab; 2: <Model>_asr.tre (gamma_multipliers: the gamma model's
+ * LAMBDA_MULTIPLIERS block, or NULL); 3: <Model>_family_results.txt (needs pvalues); 4: <Model>_clade_results.txt (the reference
+ * orders its rows by pointer value; here they come in ape order). */
+int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbed, int64_t n_families, const int32_t* states,
+                                       const double* pvalues, double pvalue_threshold, const double* gamma_multipliers, int32_t n_cat,
+                                       int32_t what, char* out, int64_t out_cap);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

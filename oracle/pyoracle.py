@@ -416,6 +416,19 @@ class RefLib:
                                                            bufs[0], len(bufs[0]), bufs[1], len(bufs[1]), bufs[2], len(bufs[2])))
             return tuple(b.value.decode() for b in bufs)
 
+        def write_reconstruction(self, lambdas, pvalues, multipliers=None, cat_probs=None):
+            """(count.tab, change.tab, asr.tre, family_results, clade_results) texts written by the reference's reconstruction."""
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            K = 0 if multipliers is None else len(multipliers)
+            mu = None if K == 0 else np.ascontiguousarray(multipliers, dtype=np.float64)
+            cp = None if K == 0 else np.ascontiguousarray(cat_probs, dtype=np.float64)
+            pv = np.ascontiguousarray(pvalues, dtype=np.float64)
+            cap = 1 << 24
+            bufs = [C.create_string_buffer(cap) for _ in range(5)]
+            self.ref.lib.ref_write_reconstruction.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, c_dp] + [C.c_char_p] * 5 + [C.c_long]
+            self.ref._check(self.ref.lib.ref_write_reconstruction(self.h, _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K, _dp(pv), *bufs, cap))
+            return tuple(b.value.decode() for b in bufs)
+
         def pvalues(self, lambdas, n_sims=1000, seed=1):
             """compute_pvalues of the unmodified reference (src/probability.cpp:528-570), randomizer_engine seeded with `seed`."""
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)

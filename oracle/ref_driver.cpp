@@ -45,6 +45,7 @@
 #include "io.h"
 #include "gene_family_reconstructor.h"
 #include "optimizer.h"
+#include "newick_ape_loader.h"
 #include "optimizer_scorer.h"
 
 INITIALIZE_EASYLOGGINGPP
@@ -406,6 +407,40 @@ int ref_write_outputs(void* h, const double* lambdas, int n_lambda, const double
             dynamic_cast<gamma_model_reconstruction*>(rec.get())->print_category_likelihoods(d, order);
         }
         if (put_text(a.str(), fam, fam_cap) || put_text(b.str(), res, res_cap) || put_text(d.str(), cat, cat_cap)) return 1;
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// The reconstruction tables as the reference writes them (reconstruction::write_results, gene_family_reconstructor.cpp:352-379) for
+// the base model (K == 0) or the gamma model at the given lambda: count.tab, change.tab, asr.tre, family_results, clade_results.
+int ref_write_reconstruction(void* h, const double* lambdas, int n_lambda, const double* multipliers, const double* cat_probs, int K,
+                             const double* pvalues, char* count, char* change, char* asr, char* famres, char* clade, long cap)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+        std::unique_ptr<model> m;
+        if (K == 0) m.reset(new base_model(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, nullptr));
+        else {
+            auto g = new gamma_model(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size,
+                                     std::vector<double>(cat_probs, cat_probs + K), std::vector<double>(multipliers, multipliers + K), nullptr);
+            g->_alpha = 1.0;
+            m.reset(g);
+            m->infer_family_likelihoods(c->ud.prior, lam.get());
+        }
+        std::unique_ptr<reconstruction> rec(m->reconstruct_ancestral_states(c->ud, c->ui, &cache));
+        auto order = get_ape_order(c->tree.get());
+        branch_probabilities none;
+        std::vector<double> pv(pvalues, pvalues + c->ud.gene_families.size());
+        std::ostringstream a, b, d, e, f;
+        rec->print_node_counts(a, order);
+        rec->print_node_change(b, order);
+        rec->print_reconstructed_states(d, order, none);
+        rec->print_increases_decreases_by_family(e, order, pv);
+        rec->print_increases_decreases_by_clade(f, order);
+        if (put_text(a.str(), count, cap) || put_text(b.str(), change, cap) || put_text(d.str(), asr, cap) || put_text(e.str(), famres, cap) ||
+            put_text(f.str(), clade, cap)) return 1;
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -144,3 +144,38 @@ def test_cpp_results_writer_with_two_lambdas_and_epsilon():
                                 "Maximum possible lambda for this topology: 0.0107527",
                                 "141 values were attempted (5% rejected)"]
     assert not math.isnan(float(txt.split()[5]))
+
+
+@pytest.mark.parametrize("newick", [
+    "(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25)",
+    "((A:2.5,B:2.5,C:2.5):4,(D:3,(E:1,F:1):2):3.5)",                               # multifurcation
+    "(((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)",
+])
+@pytest.mark.parametrize("gamma", [False, True])
+def test_cpp_reconstruction_tables_reproduce_the_reference_text(ref, oracle, newick, gamma):
+    """<Model>_count.tab, _change.tab, _asr.tre and _family_results.txt: the C++ writers fed with the C oracle's Pupko states (equal to
+    the reference's, tests above) against reconstruction::write_results' own printers; node labels follow the reference's ape numbering.
+    _clade_results.txt is compared as a set of lines (the reference orders its rows by pointer value)."""
+    tree = FlatTree(newick)
+    rng = np.random.default_rng(len(newick))
+    F = 9
+    base = rng.integers(1, 20, size=F)
+    counts = np.clip(base[:, None] + rng.integers(-4, 5, size=(F, tree.n_leaves)), 0, 40).astype(np.int32)
+    mfs, mrs = 60, 45
+    prior = fam.uniform_prior(mrs)
+    lam = [0.0123]
+    ids = [str(i) for i in range(F)]
+    pv = rng.random(F)
+    cp, mu = get_gamma(3, 0.7) if gamma else (None, None)
+    rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, prior)
+    want = rctx.write_reconstruction(lam, pv, mu, cp)
+    rctx.close()
+    rec = oracle.reconstruct(tree, counts, mfs, mrs, prior, lam, mu, cp)
+    states = rec["states"]
+    got = [io_cpp.format_reconstruction(newick, ids, states, w, pvalues=pv, threshold=0.05, gamma_multipliers=mu)
+           for w in ("count", "change", "asr", "family_results", "clade_results")]
+    assert got[0] == want[0]
+    assert got[1] == want[1]
+    assert got[2] == want[2]
+    assert got[3] == want[3]
+    assert sorted(got[4].splitlines()) == sorted(want[4].splitlines())
