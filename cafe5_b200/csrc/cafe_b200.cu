@@ -5,6 +5,7 @@
 #include "launchers.h"
 #include "peak.cuh"
 #include "simulate.cuh"
+#include "viterbi.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1119,6 +1120,43 @@ int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda
             for (size_t f = 0; f < F; ++f)
                 for (int i = 0; i < n; ++i) node_sizes[f * n + i] = sizes_t[(size_t)i * F + f];
         if (n_not_at_root) *n_not_at_root = (int64_t)exhausted;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
+int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, const int32_t* states,
+                                   const uint8_t* selected, double* probs)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!lambdas || n_lambda < c->n_lambda_classes || !states || !probs) throw CudaError{"ARG: bad argument"};
+        CK(cudaSetDevice(c->device));
+        const int n = c->n_nodes;
+        const size_t Fn = (size_t)c->F * n;
+        for (size_t i = 0; i < Fn; ++i)
+            if (states[i] < 0 || states[i] > c->max_family_size) throw CudaError{"RANGE: a reconstructed state is outside the matrix"};
+        static const double one = 1.0;
+        KeyPlan kp = plan_keys(c, lambdas, &one, 1);          // the model's own lambda, no gamma multiplier (src/execute.cpp:160-168)
+        upload_plan(c, kp);
+        launch_matrices(c, (int)kp.params.size());
+        DevBuf<int32_t> d_parent, d_st;
+        DevBuf<uint8_t> d_sel;
+        DevBuf<double> d_out;
+        struct Release { DevBuf<int32_t>&a, &b; DevBuf<uint8_t>& s; DevBuf<double>& o; ~Release() { a.release(); b.release(); s.release(); o.release(); } }
+            release{d_parent, d_st, d_sel, d_out};
+        d_parent.reserve(n); d_st.reserve(Fn); d_out.reserve(Fn);
+        CK(cudaMemcpyAsync(d_parent.p, c->parent.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_st.p, states, Fn * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        if (selected) {
+            d_sel.reserve((size_t)c->F);
+            CK(cudaMemcpyAsync(d_sel.p, selected, (size_t)c->F, cudaMemcpyHostToDevice, c->stream));
+        }
+        viterbi_sum_kernel<<<(unsigned)((Fn + 255) / 256), 256, 0, c->stream>>>(c->d_arena.p, c->d_mat_of.p, d_parent.p, d_st.p,
+                                                                                 selected ? d_sel.p : nullptr, c->F, n, c->LD,
+                                                                                 c->max_family_size, d_out.p);
+        CK(cudaGetLastError());
+        d2h(c, probs, d_out.p, Fn);
+        CK(cudaStreamSynchronize(c->stream));
         return CAFE_B200_OK;
     } catch (const CudaError& e) { return fail(c, e); }
 }

@@ -435,8 +435,11 @@ inline void write_node_table(std::ostream& ost, const Tree& t, const std::vector
 
 // <Model>_asr.tre (print_reconstructed_states :302-339, newick_node :192-201, clade::write_newick src/clade.cpp:206-223); no branch
 // probabilities (no node is starred); the gamma model appends its multipliers (write_nexus_extensions, src/gamma_core.cpp:341-349)
+// branch_probs[F x n_nodes] (cafe_b200_branch_probabilities; -1 = none): a family "has" branch probabilities when any entry is >= 0,
+// and a branch is starred when its probability is below the threshold (is_significant, :315-318)
 inline void write_asr_trees(std::ostream& ost, const Tree& t, const std::vector<std::string>& ids, const int32_t* states,
-                            const std::vector<double>& gamma_multipliers = std::vector<double>())
+                            const std::vector<double>& gamma_multipliers = std::vector<double>(), const double* branch_probs = nullptr,
+                            double threshold = 0.05)
 {
     const std::vector<int> ape = ape_ids(t);
     const int n = t.n_nodes();
@@ -452,7 +455,8 @@ inline void write_asr_trees(std::ostream& ost, const Tree& t, const std::vector<
                 ost << ')';
             }
             std::ostringstream node;
-            node << node_label(t, ape, v) << "_" << st[v];
+            const bool star = branch_probs != nullptr && branch_probs[f * n + v] >= 0 && branch_probs[f * n + v] < threshold;
+            node << node_label(t, ape, v) << (star ? "*" : "") << "_" << st[v];
             if (t.parent[v] >= 0) node << ':' << t.branch_length[v];
             ost << node.str();
         };
@@ -465,6 +469,27 @@ inline void write_asr_trees(std::ostream& ost, const Tree& t, const std::vector<
         ost << "\nBEGIN LAMBDA_MULTIPLIERS;\n";
         for (double m : gamma_multipliers) ost << "  " << m << ";\n";
         ost << "END;\n\n";
+    }
+}
+
+// <Model>_branch_probabilities.tab (print_branch_probabilities :279-300): one row per family that has branch probabilities
+inline void write_branch_probabilities(std::ostream& ost, const Tree& t, const std::vector<std::string>& ids, const double* branch_probs)
+{
+    const std::vector<int> ape = ape_ids(t), order = nodes_in_ape_order(ape);
+    const int n = t.n_nodes();
+    ost << "FamilyID";
+    for (int v : order) ost << "\t" << node_label(t, ape, v);
+    ost << std::endl;
+    for (size_t f = 0; f < ids.size(); ++f) {
+        bool any = false;
+        for (int v = 0; v < n; ++v) any = any || branch_probs[f * n + v] >= 0;
+        if (!any) continue;
+        ost << ids[f];
+        for (int v : order) {
+            if (branch_probs[f * n + v] >= 0) ost << "\t" << branch_probs[f * n + v];
+            else ost << "\tN/A";
+        }
+        ost << std::endl;
     }
 }
 

@@ -130,7 +130,7 @@ int cafe_b200_io_format_family_likelihoods(const char* ids_tabbed, int64_t n_fam
 
 int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbed, int64_t n_families, const int32_t* states,
                                        const double* pvalues, double pvalue_threshold, const double* gamma_multipliers, int32_t n_cat,
-                                       int32_t what, char* out, int64_t out_cap)
+                                       const double* branch_probs, int32_t what, char* out, int64_t out_cap)
 {
     try {
         if (!newick || !states) throw std::runtime_error("null argument");
@@ -140,8 +140,10 @@ int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbe
         switch (what) {
         case 0: cafe_b200_host::write_node_table(ost, t, ids, states, false); break;
         case 1: cafe_b200_host::write_node_table(ost, t, ids, states, true); break;
-        case 2: cafe_b200_host::write_asr_trees(ost, t, ids, states, std::vector<double>(gamma_multipliers, gamma_multipliers + (gamma_multipliers ? n_cat : 0))); break;
+        case 2: cafe_b200_host::write_asr_trees(ost, t, ids, states, std::vector<double>(gamma_multipliers, gamma_multipliers + (gamma_multipliers ? n_cat : 0)),
+                                                branch_probs, pvalue_threshold); break;
         case 3: if (!pvalues) throw std::runtime_error("p-values required"); cafe_b200_host::write_family_results(ost, ids, pvalues, pvalue_threshold); break;
+        case 5: if (!branch_probs) throw std::runtime_error("branch probabilities required"); cafe_b200_host::write_branch_probabilities(ost, t, ids, branch_probs); break;
         default: cafe_b200_host::write_clade_results(ost, t, (size_t)n_families, states); break;
         }
         return put(ost.str(), out, out_cap);

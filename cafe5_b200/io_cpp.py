@@ -82,14 +82,17 @@ def format_family_likelihoods(ids, what, family_values=None, multipliers=None, c
     return buf.value.decode()
 
 
-def format_reconstruction(newick, ids, states, what, pvalues=None, threshold=0.05, gamma_multipliers=None):
-    """what: 'count' | 'change' | 'asr' | 'family_results' | 'clade_results'; states[F, n_nodes] as cafe_b200_reconstruct returns them."""
+def format_reconstruction(newick, ids, states, what, pvalues=None, threshold=0.05, gamma_multipliers=None, branch_probs=None):
+    """what: 'count' | 'change' | 'asr' | 'family_results' | 'clade_results' | 'branch_probabilities'; states[F, n_nodes] as
+    cafe_b200_reconstruct returns them; branch_probs[F, n_nodes] from Context.branch_probabilities (-1 = none)."""
     L = _lib.load()
     st = np.ascontiguousarray(states, dtype=np.int32)
     pv = None if pvalues is None else _lib.as_f64(pvalues)
     mu = None if gamma_multipliers is None else _lib.as_f64(gamma_multipliers)
+    bp = None if branch_probs is None else _lib.as_f64(branch_probs)
     buf = C.create_string_buffer(64 * st.size + (1 << 16))
     _check(L, L.cafe_b200_io_format_reconstruction(newick.encode(), "\t".join(ids).encode(), len(ids), _lib.ip(st), _lib.dp(pv), float(threshold),
-                                                  _lib.dp(mu), 0 if mu is None else len(mu),
-                                                  {"count": 0, "change": 1, "asr": 2, "family_results": 3, "clade_results": 4}[what], buf, len(buf)))
+                                                  _lib.dp(mu), 0 if mu is None else len(mu), _lib.dp(bp),
+                                                  {"count": 0, "change": 1, "asr": 2, "family_results": 3, "clade_results": 4,
+                                                   "branch_probabilities": 5}[what], buf, len(buf)))
     return buf.value.decode()

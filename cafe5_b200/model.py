@@ -204,6 +204,16 @@ class Context:
     def stream(self):
         return self.lib.cafe_b200_stream(self.h)
 
+    def branch_probabilities(self, lambdas, states, selected=None):
+        """Per-branch change probabilities (cafe_b200_branch_probabilities): [F, n_nodes], -1 for the root / unselected families."""
+        lam = _lib.as_f64(lambdas)
+        st = np.ascontiguousarray(states, dtype=np.int32)
+        sel = None if selected is None else np.ascontiguousarray(selected, dtype=np.uint8)
+        out = np.zeros((self.F, self.n_nodes))
+        self._check(self.lib.cafe_b200_branch_probabilities(self.h, _lib.dp(lam), len(lam), _lib.ip(st), _lib.up(sel), _lib.dp(out)),
+                    "branch_probabilities")
+        return out
+
     def pvalues(self, lambdas, n_sims=1000, seed=1):
         """Family-level Monte-Carlo p-values (cafe_b200_pvalues; compute_pvalues, src/probability.cpp:528-570)."""
         lam = _lib.as_f64(lambdas)

@@ -159,6 +159,12 @@ int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lamb
  * simulated families are pruned over the full state space where the reference truncates each at its largest size + max(50, size/5). */
 int cafe_b200_pvalues(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues);
 
+/* Per-branch change probabilities of the report (compute_viterbi_sum, src/gene_family_reconstructor.cpp:388-429, as estimator::execute
+ * calls it, src/execute.cpp:173-184): states[F x n_nodes] as cafe_b200_reconstruct returns them; selected[F] (NULL = every family) marks
+ * the families whose p-value is below the threshold; probs[F x n_nodes], -1 for the root and for unselected families. */
+int cafe_b200_branch_probabilities(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, const int32_t* states,
+                                   const uint8_t* selected, double* probs);
+
 /* On-disk formats: cafe5_b200/host/io.hpp through a C interface.  Host-only (no GPU needed).  Lists of
  * strings come back tab-separated in caller-owned buffers. -------------------------------------------------------------------- */
 
@@ -194,11 +200,12 @@ int cafe_b200_io_format_family_likelihoods(const char* ids_tabbed, int64_t n_fam
 /* Reconstruction tables (reconstruction::write_results, src/gene_family_reconstructor.cpp:352-379) from the states cafe_b200_reconstruct
  * returns (states[F x n_nodes], nodes in the order cafe_b200_io_parse_tree gives for `newick`), nodes labelled with the reference's
  * ape numbering.  what = 0: <Model>_count.tab; 1: <Model>_change.tab; 2: <Model>_asr.tre (gamma_multipliers: the gamma model's
- * LAMBDA_MULTIPLIERS block, or NULL); 3: <Model>_family_results.txt (needs pvalues); 4: <Model>_clade_results.txt (the reference
- * orders its rows by pointer value; here they come in ape order). */
+ * LAMBDA_MULTIPLIERS block, or NULL; branch_probs, when given, star the branches below the threshold); 3: <Model>_family_results.txt
+ * (needs pvalues); 4: <Model>_clade_results.txt (the reference orders its rows by pointer value; here they come in ape order);
+ * 5: <Model>_branch_probabilities.tab (needs branch_probs[F x n_nodes] from cafe_b200_branch_probabilities). */
 int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbed, int64_t n_families, const int32_t* states,
                                        const double* pvalues, double pvalue_threshold, const double* gamma_multipliers, int32_t n_cat,
-                                       int32_t what, char* out, int64_t out_cap);
+                                       const double* branch_probs, int32_t what, char* out, int64_t out_cap);
 
 /* Test hooks ------------------------------------------------------------------------------- */
 

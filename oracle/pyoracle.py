@@ -429,6 +429,17 @@ class RefLib:
             self.ref._check(self.ref.lib.ref_write_reconstruction(self.h, _dp(lambdas), len(lambdas), _dp(mu), _dp(cp), K, _dp(pv), *bufs, cap))
             return tuple(b.value.decode() for b in bufs)
 
+        def branch_probabilities(self, lambdas, pvalues):
+            """(probs[F, n_nodes] with -1 = none, _branch_probabilities.tab text, _asr.tre text with stars) from the reference."""
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            pv = np.ascontiguousarray(pvalues, dtype=np.float64)
+            out = np.zeros((self.F, self.n_nodes))
+            cap = 1 << 24
+            tab, asr = C.create_string_buffer(cap), C.create_string_buffer(cap)
+            self.ref.lib.ref_branch_probabilities.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_char_p, C.c_char_p, C.c_long]
+            self.ref._check(self.ref.lib.ref_branch_probabilities(self.h, _dp(lambdas), len(lambdas), _dp(pv), _dp(out), tab, asr, cap))
+            return out, tab.value.decode(), asr.value.decode()
+
         def pvalues(self, lambdas, n_sims=1000, seed=1):
             """compute_pvalues of the unmodified reference (src/probability.cpp:528-570), randomizer_engine seeded with `seed`."""
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)

@@ -445,6 +445,38 @@ int ref_write_reconstruction(void* h, const double* lambdas, int n_lambda, const
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// Branch probabilities as estimator::execute computes them (src/execute.cpp:173-184) for the base model: compute_viterbi_sum for
+// every node of every family whose p-value is below ui.pvalue.  probs: F x n_nodes (reverse level order), -1 = none.  Also returns
+// the reference's _branch_probabilities.tab and _asr.tre (with significance stars) texts.
+int ref_branch_probabilities(void* h, const double* lambdas, int n_lambda, const double* pvalues, double* probs, char* tab, char* asr, long cap)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+        cache.precalculate_matrices(get_lambda_values(lam.get()), c->tree->get_branch_lengths());
+        base_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, nullptr);
+        std::unique_ptr<reconstruction> rec(m.reconstruct_ancestral_states(c->ud, c->ui, &cache));
+        branch_probabilities bp;
+        const size_t n = c->order.size();
+        for (size_t i = 0; i < c->ud.gene_families.size(); ++i) {
+            for (size_t k = 0; k < n; ++k) probs[i * n + k] = -1.0;
+            if (pvalues[i] < c->ui.pvalue)
+                for (size_t k = 0; k < n; ++k) {
+                    auto p = compute_viterbi_sum(c->order[k], c->ud.gene_families[i], rec.get(), c->max_family_size, cache, lam.get());
+                    bp.set(c->ud.gene_families[i], c->order[k], p);
+                    if (p._is_valid) probs[i * n + k] = p._value;
+                }
+        }
+        auto order = get_ape_order(c->tree.get());
+        std::ostringstream a, b;
+        print_branch_probabilities(a, order, c->ud.gene_families, bp);
+        rec->print_reconstructed_states(b, order, bp);
+        if (put_text(a.str(), tab, cap) || put_text(b.str(), asr, cap)) return 1;
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
 // Pupko reconstruction, base model.  states: F x n_nodes ints in reverse level order (leaves = observed).
 int ref_reconstruct_base(void* h, const double* lambdas, int n_lambda, int* states)
 {

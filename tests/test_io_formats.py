@@ -179,3 +179,25 @@ def test_cpp_reconstruction_tables_reproduce_the_reference_text(ref, oracle, new
     assert got[2] == want[2]
     assert got[3] == want[3]
     assert sorted(got[4].splitlines()) == sorted(want[4].splitlines())
+
+
+def test_cpp_branch_probability_tables_reproduce_the_reference_text(ref):
+    """_branch_probabilities.tab and the starred _asr.tre: the C++ writers fed with the REFERENCE's own compute_viterbi_sum values and
+    reconstruction (the values themselves are checked on the GPU, tests/test_gpu_parity.py) against the reference's printers."""
+    newick = "(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25)"
+    tree = FlatTree(newick)
+    rng = np.random.default_rng(4)
+    F = 10
+    base = rng.integers(1, 20, size=F)
+    counts = np.clip(base[:, None] + rng.integers(-6, 7, size=(F, tree.n_leaves)), 0, 40).astype(np.int32)
+    mfs, mrs = 60, 45
+    pv = np.where(np.arange(F) % 3 == 0, 0.2, 0.01)                          # two thirds of the families are "significant"
+    rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, fam.uniform_prior(mrs))
+    probs, tab_txt, asr_txt = rctx.branch_probabilities([0.0123], pv)
+    states = rctx.reconstruct_base([0.0123])
+    rctx.close()
+    ids = [str(i) for i in range(F)]
+    assert (probs[pv >= 0.05] == -1).all() and (probs[pv < 0.05][:, :-1] >= 0).all() and (probs[:, -1] == -1).all()
+    assert io_cpp.format_reconstruction(newick, ids, states, "branch_probabilities", branch_probs=probs) == tab_txt
+    assert io_cpp.format_reconstruction(newick, ids, states, "asr", branch_probs=probs, threshold=0.05) == asr_txt
+    assert "*" in asr_txt
