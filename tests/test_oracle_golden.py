@@ -232,3 +232,57 @@ def test_mammals_subset_matches_reference_fixture(oracle, golden):
     rg = oracle.reconstruct(tree, counts[rs], mfs, mrs, prior, [0.0018], g["gamma_mult"], g["gamma_probs"])
     assert np.array_equal(rg["states"], g["ref_rec_gamma_states"][:60])
     assert max_rel(rg["averaged"], g["ref_rec_gamma_avg"][:60]) == 0.0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_is_bit_identical_to_the_live_reference_on_random_problems(oracle, ref, seed):
+    """Beyond the committed fixtures: random trees (every third with multifurcations), 1-3 lambda classes, an error model on odd
+    seeds -- the C restatement against the unmodified reference compiled into oracle/_ref, bit for bit."""
+    import re
+    rng = np.random.default_rng(500 + seed)
+    n_taxa = int(rng.integers(3, 11))
+    nodes = ["t%d" % i for i in range(n_taxa)]
+    lam_nodes = list(nodes)
+    while len(nodes) > 1:
+        k = 3 if (seed % 3 == 0 and len(nodes) >= 3 and rng.random() < 0.4) else 2
+        idx = sorted(rng.choice(len(nodes), size=k, replace=False), reverse=True)
+        parts, lparts = [], []
+        for i in idx:
+            parts.append("%s:%g" % (nodes.pop(i), round(float(rng.uniform(0.2, 8.0)), 3)))
+            lparts.append("%s:%d" % (lam_nodes.pop(i), int(rng.integers(1, 4))))
+        nodes.append("(" + ",".join(parts) + ")")
+        lam_nodes.append("(" + ",".join(lparts) + ")")
+    newick, lam_newick = nodes[0], lam_nodes[0]
+    used = sorted({int(x) for x in re.findall(r":(\d+)", lam_newick)})
+    remap = {c: i + 1 for i, c in enumerate(used)}
+    lam_newick = re.sub(r":(\d+)", lambda m: ":%d" % remap[int(m.group(1))], lam_newick)
+    n_classes = len(used)
+    lam_newick = lam_newick if n_classes > 1 else None
+    tree = FlatTree(newick, lam_newick)
+    F = int(rng.integers(1, 12))
+    base = rng.integers(0, 26, size=F)
+    counts = np.clip(base[:, None] + rng.integers(-4, 5, size=(F, tree.n_leaves)), 0, 30).astype(np.int32)
+    mfs, mrs = 50, 38
+    prior = fam.uniform_prior(mrs)
+    lambdas = [float(rng.uniform(0.001, 0.03)) for _ in range(n_classes)]
+    em = (fam.epsilon_error_model(float(rng.uniform(0.01, 0.2)), mfs)) if seed % 2 == 1 else None
+    rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, prior, lambda_newick=lam_newick, em=em)
+    rb = rctx.eval_base(lambdas)
+    ob = oracle.eval_base(tree, counts, mfs, mrs, prior, lambdas, em=em)
+    assert np.array_equal(ob["family_lnl"], rb["family_lnl"]) and (ob["neg_lnl"] == rb["neg_lnl"] or (math.isinf(ob["neg_lnl"]) and math.isinf(rb["neg_lnl"])))
+    for f in range(min(F, 3)):
+        assert np.array_equal(oracle.prune(tree, counts[f], mfs, mrs, lambdas, em=em), rctx.prune(f, lambdas))
+    cp, mu = oracle.get_gamma(int(rng.integers(2, 5)), float(rng.uniform(0.4, 2.5)))
+    rg = rctx.eval_gamma(lambdas, mu, cp)
+    og = oracle.eval_gamma(tree, counts, mfs, mrs, prior, lambdas, mu, cp, em=em)
+    assert np.array_equal(og["failed"].astype(bool), rg["failed"].astype(bool))
+    ok = ~rg["failed"].astype(bool)
+    assert np.array_equal(og["cat_lk"][ok], rg["cat_lk"][ok])
+    assert og["neg_lnl"] == rg["neg_lnl"] or (math.isinf(og["neg_lnl"]) and math.isinf(rg["neg_lnl"]))
+    rctx.close()
+    rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, prior, lambda_newick=lam_newick)   # reconstruction ignores the error model
+    assert np.array_equal(oracle.reconstruct(tree, counts, mfs, mrs, prior, lambdas)["states"], rctx.reconstruct_base(lambdas))
+    rr = rctx.reconstruct_gamma(lambdas, mu, cp)
+    orr = oracle.reconstruct(tree, counts, mfs, mrs, prior, lambdas, mu, cp)
+    assert np.array_equal(orr["cat_states"], rr["cat_states"]) and np.array_equal(orr["states"], rr["states"])
+    rctx.close()
