@@ -1,152 +1,18 @@
-// cafe_b200.cu -- host side of libcafe_b200.so: context, per-evaluation key planning, launches, C ABI.
+// cafe_b200.cu -- host side of libcafe_b200.so: context, per-evaluation key planning, launches, the likelihood-path C ABI.
 // See include/cafe_b200.h for the boundary and the reference interfaces each entry point replaces.
-#include "../../include/cafe_b200.h"
 #define CAFE_KERNELS_IMPL
-#include "launchers.h"
+#include "context.cuh"
 #include "peak.cuh"
-#include "simulate.cuh"
-#include "viterbi.cuh"
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <limits>
-#include <map>
-#include <string>
-#include <unordered_map>
-#include <vector>
 
 using namespace cafe;
 
-namespace {
-
-constexpr int DM_BK_HOST = 16;   // DM_BK of prune_dmma.cuh
-thread_local std::string g_create_error;
-
-struct CudaError { std::string msg; };
-
-#define CK(expr)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (expr);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            char buf_[512];                                                                        \
-            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            throw CudaError{buf_};                                                                 \
-        }                                                                                          \
-    } while (0)
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    void reserve(size_t n, bool zero = false)
-    {
-        if (n <= cap) return;
-        if (p) CK(cudaFree(p));
-        p = nullptr;
-        cap = 0;
-        CK(cudaMalloc(&p, n * sizeof(T)));
-        cap = n;
-        if (zero) CK(cudaMemset(p, 0, n * sizeof(T)));
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct KeyPlan {
-    std::vector<MatParam> params;          // one per distinct matrix key
-    std::vector<int32_t> mat_of;           // [K][n_nodes]
-};
-
-}  // namespace
-
-struct cafe_b200_ctx {
-    int device = 0;
-    int n_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::string err;
-
-    // tree (host copies)
-    int n_nodes = 0;
-    std::vector<int32_t> parent, leaf_col, lambda_class;
-    std::vector<double> branch_length;
-    int n_lambda_classes = 1;
-    int S = 0, R = 0, N = 0, max_family_size = 0;
-
-    // families
-    int64_t F = 0, U = 0, U_stride = 0;
-    int n_species = 0;
-    std::vector<int32_t> counts;           // F x n_species (host copy, for leaf states)
-    std::vector<int64_t> f2u;
-
-    // schedule
-    std::vector<Step> steps;
-    std::vector<StepChild> children;
-    int n_slots = 0;
-    std::vector<int32_t> leaf_row_of_node; // row in counts_t for leaf nodes
-
-    // tiling choice
-    int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
-    // pruning kernel: 2 = DMMA with the child vector resident in shared memory (default when it fits), 1 = DMMA streaming
-    // both operands (large state spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=resident|stream|dfma
-    int prune_pref = 2, prune_kind = 2;
-    bool use_dmma = true;
-    std::vector<int32_t> gemm_nodes;
-    InlineSchedule sched{};                // schedule + key index as a kernel parameter (resident kernel)
-    int n_fslots = 1;
-    int TNW = 4, WN = 2, resident_wn = 2, dmma_stages = 4;
-    size_t smem_optin = 0, smem_per_sm = 0;
-
-    // prior / error model
-    bool have_prior = false;
-    std::vector<float> prior;
-    bool have_em = false;
-    int em_rows = 0, em_maxcnt = 0;
-
-    // device buffers
-    DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;
-    DevBuf<int64_t> d_f2u;
-    DevBuf<Step> d_steps;
-    DevBuf<StepChild> d_children;
-    DevBuf<double> d_zero, d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
-    DevBuf<uint8_t> d_ok;
-    DevBuf<MatParam> d_params;
-    DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
-    DevBuf<uint8_t> d_significant, d_failed;
-    // pupko
-    DevBuf<uint16_t> d_argmax;
-    DevBuf<int32_t> d_states, d_leaf_row, d_states_f, d_cat_states_f;
-    DevBuf<double> d_avg_f;
-    int lg_n = 0;
-
-    // pinned staging
-    void* h_stage = nullptr;
-    size_t h_stage_cap = 0;
-    double* h_result = nullptr;
-
-    // stats
-    int last_launches = 0, last_mats = 0;
-    bool stats_valid = false;
-
-    void* stage(size_t bytes)
-    {
-        if (bytes > h_stage_cap) {
-            if (h_stage) cudaFreeHost(h_stage);
-            h_stage = nullptr;
-            h_stage_cap = 0;
-            CK(cudaMallocHost(&h_stage, bytes));
-            h_stage_cap = bytes;
-        }
-        return h_stage;
-    }
-};
+namespace cafe {
+std::string& create_error()
+{
+    thread_local std::string s;
+    return s;
+}
+}  // namespace cafe
 
 namespace {
 
@@ -358,6 +224,9 @@ void choose_columns(cafe_b200_ctx* c, int K)
     c->grid = (int)std::min<int64_t>(tiles, c->n_sms);
 }
 
+}  // namespace
+
+namespace cafe {
 // ---- key planning (matrix_cache_key, src/matrix_cache.h:44-63; lambda::multiply, src/lambda.h:45-48,76-84) ----
 KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* multipliers, int K)
 {
@@ -391,6 +260,9 @@ KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* m
     }
     return kp;
 }
+}  // namespace cafe
+
+namespace {
 
 void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
 {
@@ -419,6 +291,9 @@ void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
     s.valid = 1;
 }
 
+}  // namespace
+
+namespace cafe {
 void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp)
 {
     fill_inline_schedule(c, kp);
@@ -445,6 +320,9 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
     matrix_gen_kernel<<<grid, 192, c->lg_n * sizeof(double), c->stream>>>(c->d_params.p, c->d_lg.p, c->lg_n, c->N, c->LD, c->d_arena.p);
     CK(cudaGetLastError());
 }
+}  // namespace cafe
+
+namespace {
 
 void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
@@ -570,12 +448,10 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
     return true;
 }
 
-template <typename T>
-void d2h(cafe_b200_ctx* c, T* dst, const T* src, size_t n)
-{
-    if (dst && n) CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
-}
 
+}  // namespace
+
+namespace cafe {
 int fail(cafe_b200_ctx* c, const CudaError& e)
 {
     int code = CAFE_B200_ERR_CUDA;
@@ -583,9 +459,12 @@ int fail(cafe_b200_ctx* c, const CudaError& e)
     if (m.rfind("ARG: ", 0) == 0) { code = CAFE_B200_ERR_ARG; m = m.substr(5); }
     else if (m.rfind("RANGE: ", 0) == 0) { code = CAFE_B200_ERR_RANGE; m = m.substr(7); }
     else if (m.rfind("STATE: ", 0) == 0) { code = CAFE_B200_ERR_STATE; m = m.substr(7); }
-    if (c) c->err = m; else g_create_error = m;
+    if (c) c->err = m; else create_error() = m;
     return code;
 }
+}  // namespace cafe
+
+namespace {
 
 }  // namespace
 
@@ -718,7 +597,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         if (c) cafe_b200_destroy(c);
         return code;
     } catch (const std::exception& e) {
-        g_create_error = e.what();
+        create_error() = e.what();
         if (c) cafe_b200_destroy(c);
         return CAFE_B200_ERR_ARG;
     }
@@ -744,7 +623,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     return CAFE_B200_OK;
 }
 
-const char* cafe_b200_last_error(const cafe_b200_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+const char* cafe_b200_last_error(const cafe_b200_ctx* c) { return c ? c->err.c_str() : create_error().c_str(); }
 
 int cafe_b200_set_prior(cafe_b200_ctx* c, const float* prior, int32_t n)
 {
@@ -1055,172 +934,6 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         CK(cudaStreamSynchronize(c->stream));
         return CAFE_B200_OK;
     } catch (const CudaError& e) { return fail(c, e); }
-}
-
-int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
-                       int32_t n_cat, int32_t max_sim, int32_t max_redraws, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
-                       int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root)
-{
-    if (!c) return CAFE_B200_ERR_ARG;
-    try {
-        if (!lambdas || n_lambda < c->n_lambda_classes || !root_sizes || n_families <= 0 || !counts) throw CudaError{"ARG: bad argument"};
-        if (n_cat > 0 && (!multipliers || !cat_probs)) throw CudaError{"ARG: gamma simulation needs multipliers and cat_probs"};
-        if (max_sim < 2 || max_sim > c->N) throw CudaError{"RANGE: max_sim must be in [2, matrix size]"};
-        CK(cudaSetDevice(c->device));
-        const int K = n_cat > 0 ? n_cat : 1;
-        static const double one = 1.0;
-        const double* mult = n_cat > 0 ? multipliers : &one;
-        const double* probs = n_cat > 0 ? cat_probs : &one;
-        KeyPlan kp = plan_keys(c, lambdas, mult, K);
-        upload_plan(c, kp);
-        const int n_mats = (int)kp.params.size();
-        launch_matrices(c, n_mats);
-        const int n = c->n_nodes;
-        const size_t F = (size_t)n_families;
-        DevBuf<double> d_cdf, d_probs;
-        DevBuf<int32_t> d_parent, d_leaf_col, d_root, d_sizes, d_counts, d_cat;
-        DevBuf<uint8_t> d_has;
-        DevBuf<unsigned long long> d_exh;
-        struct Release {   // scratch of one call: freed on every exit path
-            DevBuf<double>&a, &b; DevBuf<int32_t>&c1, &c2, &c3, &c4, &c5, &c6; DevBuf<uint8_t>& d; DevBuf<unsigned long long>& e;
-            ~Release() { a.release(); b.release(); c1.release(); c2.release(); c3.release(); c4.release(); c5.release(); c6.release(); d.release(); e.release(); }
-        } release{d_cdf, d_probs, d_parent, d_leaf_col, d_root, d_sizes, d_counts, d_cat, d_has, d_exh};
-        d_cdf.reserve((size_t)n_mats * max_sim * c->N);
-        d_probs.reserve(K);
-        d_parent.reserve(n); d_leaf_col.reserve(n);
-        d_root.reserve(F); d_sizes.reserve(F * n); d_counts.reserve(F * c->n_species); d_cat.reserve(F);
-        d_has.reserve(F * n);
-        d_exh.reserve(1, true);
-        CK(cudaMemcpyAsync(d_probs.p, probs, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(d_parent.p, c->parent.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(d_leaf_col.p, c->leaf_col.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(d_root.p, root_sizes, F * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(d_counts.p, 0, F * c->n_species * sizeof(int32_t), c->stream));
-        sim_cdf_kernel<<<n_mats, 256, 0, c->stream>>>(c->d_arena.p, c->LD, c->N, max_sim, d_cdf.p);
-        CK(cudaGetLastError());
-        SimParams sp{};
-        sp.parent = d_parent.p; sp.leaf_col = d_leaf_col.p; sp.mat_of = c->d_mat_of.p; sp.cdf = d_cdf.p; sp.cat_probs = d_probs.p;
-        sp.root_sizes = d_root.p; sp.sizes = d_sizes.p; sp.has = d_has.p; sp.counts = d_counts.p; sp.categories = d_cat.p;
-        sp.exhausted = d_exh.p; sp.F = n_families; sp.seed = seed;
-        sp.n_nodes = n; sp.n_species = c->n_species; sp.K = K; sp.N = c->N; sp.max_sim = max_sim;
-        sp.max_attempts = 1 + std::max(max_redraws, 0);
-        simulate_kernel<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>(sp);
-        CK(cudaGetLastError());
-        d2h(c, counts, d_counts.p, F * c->n_species);
-        d2h(c, categories, d_cat.p, F);
-        unsigned long long exhausted = 0;
-        CK(cudaMemcpyAsync(&exhausted, d_exh.p, sizeof exhausted, cudaMemcpyDeviceToHost, c->stream));
-        std::vector<int32_t> sizes_t;
-        if (node_sizes) {
-            sizes_t.resize(F * n);
-            CK(cudaMemcpyAsync(sizes_t.data(), d_sizes.p, F * n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        }
-        CK(cudaStreamSynchronize(c->stream));
-        if (node_sizes)
-            for (size_t f = 0; f < F; ++f)
-                for (int i = 0; i < n; ++i) node_sizes[f * n + i] = sizes_t[(size_t)i * F + f];
-        if (n_not_at_root) *n_not_at_root = (int64_t)exhausted;
-        return CAFE_B200_OK;
-    } catch (const CudaError& e) { return fail(c, e); }
-}
-
-int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, const int32_t* states,
-                                   const uint8_t* selected, double* probs)
-{
-    if (!c) return CAFE_B200_ERR_ARG;
-    try {
-        if (!lambdas || n_lambda < c->n_lambda_classes || !states || !probs) throw CudaError{"ARG: bad argument"};
-        CK(cudaSetDevice(c->device));
-        const int n = c->n_nodes;
-        const size_t Fn = (size_t)c->F * n;
-        for (size_t i = 0; i < Fn; ++i)
-            if (states[i] < 0 || states[i] > c->max_family_size) throw CudaError{"RANGE: a reconstructed state is outside the matrix"};
-        static const double one = 1.0;
-        KeyPlan kp = plan_keys(c, lambdas, &one, 1);          // the model's own lambda, no gamma multiplier (src/execute.cpp:160-168)
-        upload_plan(c, kp);
-        launch_matrices(c, (int)kp.params.size());
-        DevBuf<int32_t> d_parent, d_st;
-        DevBuf<uint8_t> d_sel;
-        DevBuf<double> d_out;
-        struct Release { DevBuf<int32_t>&a, &b; DevBuf<uint8_t>& s; DevBuf<double>& o; ~Release() { a.release(); b.release(); s.release(); o.release(); } }
-            release{d_parent, d_st, d_sel, d_out};
-        d_parent.reserve(n); d_st.reserve(Fn); d_out.reserve(Fn);
-        CK(cudaMemcpyAsync(d_parent.p, c->parent.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(d_st.p, states, Fn * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        if (selected) {
-            d_sel.reserve((size_t)c->F);
-            CK(cudaMemcpyAsync(d_sel.p, selected, (size_t)c->F, cudaMemcpyHostToDevice, c->stream));
-        }
-        viterbi_sum_kernel<<<(unsigned)((Fn + 255) / 256), 256, 0, c->stream>>>(c->d_arena.p, c->d_mat_of.p, d_parent.p, d_st.p,
-                                                                                 selected ? d_sel.p : nullptr, c->F, n, c->LD,
-                                                                                 c->max_family_size, d_out.p);
-        CK(cudaGetLastError());
-        d2h(c, probs, d_out.p, Fn);
-        CK(cudaStreamSynchronize(c->stream));
-        return CAFE_B200_OK;
-    } catch (const CudaError& e) { return fail(c, e); }
-}
-
-int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues)
-{
-    if (!c) return CAFE_B200_ERR_ARG;
-    cafe_b200_ctx* sim = nullptr;
-    try {
-        if (!lambdas || n_lambda < c->n_lambda_classes || n_sims < 1 || !pvalues) throw CudaError{"ARG: bad argument"};
-        if (!c->have_prior) throw CudaError{"STATE: set_prior must be called first"};
-        const int R = c->R, n = c->n_nodes;
-        // 1. conditional distributions: n_sims families per root size 1..R, no redraws, no error model (get_random_probabilities,
-        //    create_family: src/probability.cpp:355-375,434-447), child sizes below max_family_size
-        const size_t Fs = (size_t)R * n_sims;
-        std::vector<int32_t> roots(Fs), sim_counts(Fs * c->n_species);
-        for (int r = 0; r < R; ++r) std::fill(roots.begin() + (size_t)r * n_sims, roots.begin() + (size_t)(r + 1) * n_sims, r + 1);
-        int rc = cafe_b200_simulate(c, lambdas, n_lambda, nullptr, nullptr, 0, c->max_family_size, 0, roots.data(), (int64_t)Fs, seed,
-                                    sim_counts.data(), nullptr, nullptr, nullptr);
-        if (rc != CAFE_B200_OK) return rc;
-        // 2. their likelihood at the root size they were generated from (compute_family_probabilities, :377-432; the reference
-        //    truncates each family's state space at its largest size + max(50, size/5), we keep the full space)
-        cafe_b200_tree t{n, c->parent.data(), c->branch_length.data(), c->leaf_col.data(), c->lambda_class.data()};
-        rc = cafe_b200_create(&t, sim_counts.data(), (int64_t)Fs, c->n_species, c->max_family_size, R, c->device, &sim);
-        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulated context: ") + g_create_error};
-        rc = cafe_b200_set_prior(sim, c->prior.data(), (int32_t)c->prior.size());
-        std::vector<double> vec(Fs * R);
-        if (rc == CAFE_B200_OK) rc = cafe_b200_root_vectors(sim, lambdas, n_lambda, 1.0, vec.data());
-        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulated families: ") + sim->err};
-        cafe_b200_destroy(sim);
-        sim = nullptr;
-        std::vector<std::vector<double>> cond(R, std::vector<double>(n_sims));
-        for (int r = 0; r < R; ++r) {
-            for (int i = 0; i < n_sims; ++i) cond[r][i] = vec[((size_t)r * n_sims + i) * R + r];   // index r <-> root size r+1
-            std::sort(cond[r].begin(), cond[r].end());
-        }
-        // 3. observed families: root vectors without the error model (compute_pvalues passes NULL, :549), then
-        //    find_best_pvalue (:513-526) over root sizes below rint(1.25 * largest count)
-        const bool had_em = c->have_em;
-        c->have_em = false;
-        vec.assign((size_t)c->F * R, 0.0);
-        rc = cafe_b200_root_vectors(c, lambdas, n_lambda, 1.0, vec.data());
-        c->have_em = had_em;
-        if (rc != CAFE_B200_OK) return rc;
-        for (int64_t f = 0; f < c->F; ++f) {
-            int mx = 0;
-            for (int j = 0; j < c->n_species; ++j) mx = std::max(mx, c->counts[(size_t)f * c->n_species + j]);
-            const int limit = std::min((int)std::rint(mx * 1.25), R);
-            double best = 0.0;
-            for (int j = 0; j < limit; ++j) {
-                const std::vector<double>& d = cond[j];
-                const double v = vec[(size_t)f * R + j];
-                size_t idx = d.size() - 1;
-                auto bound = std::upper_bound(d.begin(), d.end(), v);
-                if (bound != d.end()) idx = (size_t)(bound - d.begin());
-                best = std::max(best, (double)idx / (double)d.size());
-            }
-            pvalues[f] = best;
-        }
-        return CAFE_B200_OK;
-    } catch (const CudaError& e) {
-        if (sim) cafe_b200_destroy(sim);
-        return fail(c, e);
-    }
 }
 
 }  // extern "C"

@@ -1,0 +1,164 @@
+// context.cuh -- the context behind the opaque cafe_b200_ctx handle and the host helpers the translation units of libcafe_b200.so
+// share: error plumbing, device buffers, the per-evaluation matrix-key plan.  cafe_b200.cu owns the likelihood path (create, set_*,
+// eval_*, reconstruct, test hooks); abi_analysis.cu builds the simulator, the p-values and the branch probabilities on top of it.
+#pragma once
+#include "../../include/cafe_b200.h"
+#include "launchers.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace cafe {
+
+constexpr int DM_BK_HOST = 16;   // DM_BK of prune_dmma.cuh
+std::string& create_error();          // last failed cafe_b200_create on this thread
+
+struct CudaError { std::string msg; };
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw cafe::CudaError{buf_};                                                                 \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n, bool zero = false)
+    {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+        if (zero) CK(cudaMemset(p, 0, n * sizeof(T)));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct KeyPlan {
+    std::vector<MatParam> params;          // one per distinct matrix key
+    std::vector<int32_t> mat_of;           // [K][n_nodes]
+};
+
+}  // namespace cafe
+
+struct cafe_b200_ctx {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // tree (host copies)
+    int n_nodes = 0;
+    std::vector<int32_t> parent, leaf_col, lambda_class;
+    std::vector<double> branch_length;
+    int n_lambda_classes = 1;
+    int S = 0, R = 0, N = 0, max_family_size = 0;
+
+    // families
+    int64_t F = 0, U = 0, U_stride = 0;
+    int n_species = 0;
+    std::vector<int32_t> counts;           // F x n_species (host copy, for leaf states)
+    std::vector<int64_t> f2u;
+
+    // schedule
+    std::vector<cafe::Step> steps;
+    std::vector<cafe::StepChild> children;
+    int n_slots = 0;
+    std::vector<int32_t> leaf_row_of_node; // row in counts_t for leaf nodes
+
+    // tiling choice
+    int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;
+    // pruning kernel: 2 = DMMA with the child vector resident in shared memory (default when it fits), 1 = DMMA streaming
+    // both operands (large state spaces), 0 = DFMA register tiles.  CAFE_B200_PRUNE=resident|stream|dfma
+    int prune_pref = 2, prune_kind = 2;
+    bool use_dmma = true;
+    std::vector<int32_t> gemm_nodes;
+    cafe::InlineSchedule sched{};                // schedule + key index as a kernel parameter (resident kernel)
+    int n_fslots = 1;
+    int TNW = 4, WN = 2, resident_wn = 2, dmma_stages = 4;
+    size_t smem_optin = 0, smem_per_sm = 0;
+
+    // prior / error model
+    bool have_prior = false;
+    std::vector<float> prior;
+    bool have_em = false;
+    int em_rows = 0, em_maxcnt = 0;
+
+    // device buffers
+    cafe::DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;
+    cafe::DevBuf<int64_t> d_f2u;
+    cafe::DevBuf<cafe::Step> d_steps;
+    cafe::DevBuf<cafe::StepChild> d_children;
+    cafe::DevBuf<double> d_zero, d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
+    cafe::DevBuf<uint8_t> d_ok;
+    cafe::DevBuf<cafe::MatParam> d_params;
+    cafe::DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
+    cafe::DevBuf<uint8_t> d_significant, d_failed;
+    // pupko
+    cafe::DevBuf<uint16_t> d_argmax;
+    cafe::DevBuf<int32_t> d_states, d_leaf_row, d_states_f, d_cat_states_f;
+    cafe::DevBuf<double> d_avg_f;
+    int lg_n = 0;
+
+    // pinned staging
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    double* h_result = nullptr;
+
+    // stats
+    int last_launches = 0, last_mats = 0;
+    bool stats_valid = false;
+
+    void* stage(size_t bytes)
+    {
+        if (bytes > h_stage_cap) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr;
+            h_stage_cap = 0;
+            CK(cudaMallocHost(&h_stage, bytes));
+            h_stage_cap = bytes;
+        }
+        return h_stage;
+    }
+};
+
+
+namespace cafe {
+
+// matrix_cache_key planning for one evaluation (src/matrix_cache.h:44-63; lambda::multiply, src/lambda.h:45-48,76-84)
+KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* multipliers, int K);
+// key parameters + key index -> device (and the kernel-parameter copy of the schedule); grows the matrix arena
+void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp);
+void launch_matrices(cafe_b200_ctx* c, int n_mats);
+// CudaError -> status code; stores the message in the context (or as the thread's create error)
+int fail(cafe_b200_ctx* c, const CudaError& e);
+
+template <typename T>
+void d2h(cafe_b200_ctx* c, T* dst, const T* src, size_t n)
+{
+    if (dst && n) CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+}
+
+}  // namespace cafe
