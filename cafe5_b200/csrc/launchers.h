@@ -1,6 +1,6 @@
 // launchers.h -- host-callable launchers of the templated kernels.  Each family of instantiations lives in its own
-// translation unit (tu_*.cu) so the library builds in parallel; cafe_b200.cu holds the context, the C ABI and the
-// small non-template kernels.
+// translation unit (tu_*.cu) so the library builds in parallel; cafe_b200.cu holds the likelihood-path C ABI and the
+// small non-template kernels, context.cuh the context they share with abi_analysis.cu.
 #pragma once
 #include "kernels.cuh"
 #include "pupko.cuh"
