@@ -412,7 +412,7 @@ def run_ours(args):
             "config": workload_config(args, tree),
             "e2e": {"value": e2e_value, "unit": "family-likelihood evals/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_per_step},
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": int(ctx.last_stats()["launches"]) * args.steps,
             "roofline": {"bound": "tensor", "kernel": prune_kernel_name(), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                          "peak_source": "FP64 tensor pipe (DMMA; tcgen05 has no FP64 kind) measured live on this GPU by "

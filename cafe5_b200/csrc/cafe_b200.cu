@@ -316,8 +316,27 @@ void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp)
 
 void launch_matrices(cafe_b200_ctx* c, int n_mats)
 {
-    dim3 grid(c->N, n_mats);
-    matrix_gen_kernel<<<grid, 192, c->lg_n * sizeof(double), c->stream>>>(c->d_params.p, c->d_lg.p, c->lg_n, c->N, c->LD, c->d_arena.p);
+    const size_t rows_smem = matrix_gen_rows_smem(c->N);
+    if (c->matgen_entry || rows_smem > 200 * 1024) {   // state spaces whose tables do not fit shared memory (N > 2300) take the per-entry kernel
+        dim3 grid(c->N, n_mats);
+        matrix_gen_kernel<<<grid, 192, c->lg_n * sizeof(double), c->stream>>>(c->d_params.p, c->d_lg.p, c->lg_n, c->N, c->LD, c->d_arena.p);
+        CK(cudaGetLastError());
+        return;
+    }
+    c->d_powtab.reserve((size_t)n_mats * c->N);
+    pow_table_kernel<<<(n_mats + 127) / 128, 128, 0, c->stream>>>(c->d_params.p, n_mats, c->N, c->d_powtab.p);
+    CK(cudaGetLastError());
+    dim3 grid((c->N + MG_S - 1) / MG_S, n_mats);
+    if (rows_smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(matrix_gen_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+        CK(cudaFuncSetAttribute(matrix_gen_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+    }
+    if (c->matgen_libexp)
+        matrix_gen_rows_kernel<true><<<grid, 192, matrix_gen_rows_smem(c->N), c->stream>>>(c->d_params.p, c->d_powtab.p, n_mats, c->d_lg.p, c->N,
+                                                                                           c->LD, c->d_arena.p);
+    else
+        matrix_gen_rows_kernel<false><<<grid, 192, matrix_gen_rows_smem(c->N), c->stream>>>(c->d_params.p, c->d_powtab.p, n_mats, c->d_lg.p, c->N,
+                                                                                            c->LD, c->d_arena.p);
     CK(cudaGetLastError());
 }
 }  // namespace cafe
@@ -443,7 +462,7 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
         final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, c->d_partial_fail.p, nb, c->d_result.p);
     }
     CK(cudaGetLastError());
-    c->last_launches = 4;
+    c->last_launches = c->matgen_entry ? 4 : 5;   // [pow table +] matrices, pruning, finish, final sum
     c->stats_valid = true;
     return true;
 }
@@ -512,6 +531,8 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->smem_optin = prop.sharedMemPerBlockOptin;
         c->smem_per_sm = prop.sharedMemPerMultiprocessor;
         if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = v == 4 ? 4 : 2; }
+        if (const char* e = std::getenv("CAFE_B200_PUPKO_THREADS")) c->pupko_threads = std::atoi(e) == 256 ? 256 : 512;
+        if (const char* e = std::getenv("CAFE_B200_MATGEN")) { c->matgen_entry = std::strcmp(e, "entry") == 0; c->matgen_libexp = std::strcmp(e, "rows") == 0; }
         if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
             const std::string v(e);
             c->use_dmma = v != "dfma";
@@ -610,7 +631,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
     c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
-    c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release();
+    c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release(); c->d_powtab.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
     c->d_partial.release(); c->d_partial_fail.release(); c->d_result.release(); c->d_roots.release();
     c->d_significant.release(); c->d_failed.release(); c->d_argmax.release(); c->d_states.release();
@@ -911,7 +932,7 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         p.LD = c->LD; p.S = c->S; p.R = c->R; p.N = c->N; p.K = K;
         p.root_len = std::min(c->max_family_size, c->R) + 1;
         p.n_col_tiles = c->n_col_tiles; p.n_mtiles = c->n_mtiles;
-        CK(launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p));
+        CK(launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p, c->pupko_threads));
         const int n = c->n_nodes;
         const size_t Fn = (size_t)c->F * n;
         c->d_cat_probs.reserve(K);

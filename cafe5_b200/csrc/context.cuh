@@ -114,6 +114,10 @@ struct cafe_b200_ctx {
     cafe::DevBuf<double> d_zero, d_lg, d_arena, d_scratch, d_prior, d_logprior, d_em, d_best, d_cat_probs;
     cafe::DevBuf<uint8_t> d_ok;
     cafe::DevBuf<cafe::MatParam> d_params;
+    cafe::DevBuf<double> d_powtab;               // [N][n_mats] pow(coeff, j) of every key (pow_table_kernel)
+    int pupko_threads = 512;                     // CAFE_B200_PUPKO_THREADS=256: the two-warps-per-sub-partition comparison geometry
+    bool matgen_entry = false;                   // CAFE_B200_MATGEN=entry: the one-thread-per-entry comparison kernel
+    bool matgen_libexp = false;                  // CAFE_B200_MATGEN=rows: the default kernel with the library exp() per term
     cafe::DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
     cafe::DevBuf<uint8_t> d_significant, d_failed;
     // pupko

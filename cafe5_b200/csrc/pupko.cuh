@@ -25,11 +25,18 @@ struct PupkoParams {
     int32_t n_col_tiles, n_mtiles;
 };
 
-template <int TM, int TN>
-__global__ void __launch_bounds__(PRUNE_THREADS, 1)
+// Geometry: 16 thread-rows x (THREADS / 16) thread-columns; a thread owns TM rows (i * 16 + tm) and CT = BN / (THREADS / 16) columns.
+//   THREADS = 512 (default for BN >= 32): a warp is one thread-row, so the matrix operand is a broadcast load, and a thread carries
+//                 TM x CT <= 13 x 2 (value, argmax) pairs in <= 128 registers: 4 warps per sub-partition hide the compare / select
+//                 latency chain (the 256-thread geometry ran 2 warps per sub-partition at 226 registers: FP64 pipe 34 % active).
+//   THREADS = 256: BN = 16 (few families), and the comparison geometry (CAFE_B200_PUPKO_THREADS=256).
+template <int TM, int TN, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 pupko_kernel(const PupkoParams p)
 {
     constexpr int BM = 16 * TM, BN = 16 * TN, BK = PRUNE_BK, STAGES = PRUNE_STAGES;
+    constexpr int NTN = THREADS / 16, CT = BN / NTN;
+    static_assert(CT * NTN == BN && CT >= 1, "column tile does not divide");
     extern __shared__ __align__(16) double smem[];
     const int kpad = (p.S + BK - 1) / BK * BK;
     double* Ms = smem;                                   // [kpad][BN]  prod_children L_child[j]
@@ -37,7 +44,7 @@ pupko_kernel(const PupkoParams p)
     int32_t* st_s = reinterpret_cast<int32_t*>(As + (size_t)STAGES * BK * BM);   // [n_steps][BN] traceback states
 
     const int tid = threadIdx.x;
-    const int tn = tid & 15, tm = tid >> 4;
+    const int tn = tid % NTN, tm = tid / NTN;
     const int n_tiles = p.K * p.n_col_tiles;
     double* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * p.slot_stride;
     uint16_t* const my_arg = p.argmax + (size_t)blockIdx.x * p.n_steps * p.arg_stride;
@@ -57,7 +64,7 @@ pupko_kernel(const PupkoParams p)
                 if (ch.leaf_row >= 0) {
                     // reconstruct_leaf_node (:30-46): L[j] = P(j -> obs) = PT[obs][j]; one warp per column, j coalesced
                     const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
-                    for (int c = tid >> 5; c < BN; c += PRUNE_THREADS / 32) {
+                    for (int c = tid >> 5; c < BN; c += THREADS / 32) {
                         int64_t u = col0 + c;
                         if (u >= p.U) u = p.U - 1;
                         const int obs = p.counts_t[(size_t)ch.leaf_row * p.U_stride + u];
@@ -69,7 +76,7 @@ pupko_kernel(const PupkoParams p)
                     }
                 } else {
                     const double* __restrict__ src = my_scratch + (size_t)ch.slot * p.slot_stride;
-                    for (int idx = tid; idx < kpad * BN; idx += PRUNE_THREADS) {
+                    for (int idx = tid; idx < kpad * BN; idx += THREADS) {
                         const double l = (idx / BN) < p.S ? src[idx] : 0.0;
                         Ms[idx] = ci == 0 ? l : __dmul_rn(Ms[idx], l);
                     }
@@ -97,18 +104,18 @@ pupko_kernel(const PupkoParams p)
             uint16_t* const out_arg = my_arg + (size_t)st * p.arg_stride;
             for (int mt = 0; mt < p.n_mtiles; ++mt) {
                 const int m0 = mt * BM;
-                double best[TM][TN];
-                int arg[TM][TN];
+                double best[TM][CT];
+                int arg[TM][CT];
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) { best[i][j] = -1.0; arg[i][j] = 0; }
+                    for (int j = 0; j < CT; ++j) { best[i][j] = -1.0; arg[i][j] = 0; }
                 if (mt > 0) __syncthreads();
                 auto load_chunk = [&](int chunk) {
                     if (chunk < n_chunks) {
                         double* dst = As + (size_t)(chunk % STAGES) * BK * BM;
                         const double* __restrict__ g = PT + (size_t)chunk * BK * p.LD + m0;
-                        for (int idx = tid; idx < BK * BM / 2; idx += PRUNE_THREADS) {
+                        for (int idx = tid; idx < BK * BM / 2; idx += THREADS) {
                             const int kk = idx / (BM / 2), mm = (idx % (BM / 2)) * 2;
                             cp_async16(dst + kk * BM + mm, g + (size_t)kk * p.LD + mm);
                         }
@@ -126,15 +133,15 @@ pupko_kernel(const PupkoParams p)
 #pragma unroll
                     for (int kk = 0; kk < BK; ++kk) {
                         const int jj = chunk * BK + kk;
-                        double a[TM], b[TN];
+                        double a[TM], b[CT];
 #pragma unroll
                         for (int i = 0; i < TM; ++i) a[i] = a_s[kk * BM + i * 16];
 #pragma unroll
-                        for (int j = 0; j < TN; ++j) b[j] = b_s[kk * BN + col_of<TN>(tn, j)];
+                        for (int j = 0; j < CT; ++j) b[j] = b_s[kk * BN + col_of<CT>(tn, j)];
 #pragma unroll
                         for (int i = 0; i < TM; ++i)
 #pragma unroll
-                            for (int j = 0; j < TN; ++j) {
+                            for (int j = 0; j < CT; ++j) {
                                 const double val = __dmul_rn(b[j], a[i]);   // value * matrix->get(i, j)
                                 if (val > best[i][j]) { best[i][j] = val; arg[i][j] = jj; }
                             }
@@ -144,8 +151,8 @@ pupko_kernel(const PupkoParams p)
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) {
-                        const size_t o = (size_t)(m0 + i * 16 + tm) * BN + col_of<TN>(tn, j);
+                    for (int j = 0; j < CT; ++j) {
+                        const size_t o = (size_t)(m0 + i * 16 + tm) * BN + col_of<CT>(tn, j);
                         out_slot[o] = best[i][j];
                         out_arg[o] = (uint16_t)arg[i][j];
                     }
@@ -179,32 +186,38 @@ inline size_t pupko_smem(int S, int n_steps)
 }
 
 template <int TM, int TN>
-inline void launch_pupko_t(int grid, int S, cudaStream_t stream, const PupkoParams& p)
+inline void launch_pupko_t(int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
     size_t smem = pupko_smem<TM, TN>(S, p.n_steps);
-    cudaFuncSetAttribute(pupko_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pupko_kernel<TM, TN><<<grid, PRUNE_THREADS, smem, stream>>>(p);
-}
-
-template <int TN>
-inline void launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const PupkoParams& p)
-{
-    switch (TM) {
-    case 8: launch_pupko_t<8, TN>(grid, S, stream, p); break;
-    case 9: launch_pupko_t<9, TN>(grid, S, stream, p); break;
-    case 10: launch_pupko_t<10, TN>(grid, S, stream, p); break;
-    case 11: launch_pupko_t<11, TN>(grid, S, stream, p); break;
-    case 12: launch_pupko_t<12, TN>(grid, S, stream, p); break;
-    default: launch_pupko_t<13, TN>(grid, S, stream, p); break;
+    if (TN >= 2 && threads == 512) {
+        constexpr int T = TN >= 2 ? 512 : 256;      // (TN = 1 never instantiates the 512-thread geometry)
+        cudaFuncSetAttribute(pupko_kernel<TM, TN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pupko_kernel<TM, TN, T><<<grid, T, smem, stream>>>(p);
+    } else {
+        cudaFuncSetAttribute(pupko_kernel<TM, TN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pupko_kernel<TM, TN, 256><<<grid, 256, smem, stream>>>(p);
     }
 }
 
-inline void launch_pupko_impl(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p)
+template <int TN>
+inline void launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
+{
+    switch (TM) {
+    case 8: launch_pupko_t<8, TN>(grid, S, stream, p, threads); break;
+    case 9: launch_pupko_t<9, TN>(grid, S, stream, p, threads); break;
+    case 10: launch_pupko_t<10, TN>(grid, S, stream, p, threads); break;
+    case 11: launch_pupko_t<11, TN>(grid, S, stream, p, threads); break;
+    case 12: launch_pupko_t<12, TN>(grid, S, stream, p, threads); break;
+    default: launch_pupko_t<13, TN>(grid, S, stream, p, threads); break;
+    }
+}
+
+inline void launch_pupko_impl(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
     switch (TN) {
-    case 4: launch_pupko_tn<4>(TM, grid, S, stream, p); break;
-    case 2: launch_pupko_tn<2>(TM, grid, S, stream, p); break;
-    default: launch_pupko_tn<1>(TM, grid, S, stream, p); break;
+    case 4: launch_pupko_tn<4>(TM, grid, S, stream, p, threads); break;
+    case 2: launch_pupko_tn<2>(TM, grid, S, stream, p, threads); break;
+    default: launch_pupko_tn<1>(TM, grid, S, stream, p, threads); break;
     }
 }
 

@@ -3,9 +3,9 @@
 #include "launchers.h"
 
 namespace cafe {
-cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p)
+cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
-    launch_pupko_impl(TM, TN, grid, S, stream, p);
+    launch_pupko_impl(TM, TN, grid, S, stream, p, threads);
     return cudaGetLastError();
 }
 }  // namespace cafe
