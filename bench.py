@@ -335,7 +335,7 @@ def run_ours(args):
     d2h = counts.shape[0] * (K * 8 + 8 + K * 8 + K + 1) + 16
     for i in range(2):
         lam, alpha, cp, mu = step_params(100 + i, K)
-        ctx.eval_gamma([lam], alpha, mu, cp)
+        ctx.eval_gamma([lam], alpha, mu, cp, pinned=True)
     barrier()
     e2e_ms = []
     for i in range(args.steps):
@@ -343,7 +343,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         ctx.set_prior(prior)                        # host buffers in, every step
         ctx.set_error_model(None)
-        out = ctx.eval_gamma([lam], alpha, mu, cp)  # all per-family outputs back to host memory
+        out = ctx.eval_gamma([lam], alpha, mu, cp, pinned=True)  # all per-family outputs back to (page-locked) host memory
         tot_i, _ = cdist.allreduce_score(out["neg_lnl"], out["n_failed"])
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     barrier()

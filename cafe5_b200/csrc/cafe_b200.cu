@@ -794,6 +794,24 @@ int cafe_b200_describe(const cafe_b200_ctx* c, int64_t* n_families, int32_t* n_n
     return CAFE_B200_OK;
 }
 
+int cafe_b200_host_alloc(size_t bytes, void** out)
+{
+    try {
+        if (!out) throw CudaError{"ARG: null output"};
+        *out = nullptr;
+        CK(cudaMallocHost(out, bytes ? bytes : 1));
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(nullptr, e); }
+}
+
+int cafe_b200_host_free(void* p)
+{
+    try {
+        if (p) CK(cudaFreeHost(p));
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(nullptr, e); }
+}
+
 int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops)
 {
     try {

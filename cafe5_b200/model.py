@@ -113,6 +113,9 @@ class Context:
         if getattr(self, "h", None):
             self.lib.cafe_b200_destroy(self.h)
             self.h = None
+        for _, ptr in getattr(self, "_pinned_bufs", {}).values():
+            self.lib.cafe_b200_host_free(ptr)
+        self._pinned_bufs = {}
 
     def __del__(self):
         try:
@@ -145,7 +148,24 @@ class Context:
         self._check(self.lib.cafe_b200_eval_base(self.h, _lib.dp(lam), len(lam), C.byref(neg), _lib.dp(fam)), "eval_base")
         return neg.value, fam
 
-    def eval_gamma(self, lambdas, alpha, multipliers, cat_probs, want_family=True):
+    def _pinned(self, name, shape, dtype):
+        """A page-locked output buffer owned by this context (cafe_b200_host_alloc), allocated once per (name, shape) and REUSED by
+        later calls - like the reference's model::results / gamma_model::_category_likelihoods, which are members overwritten by
+        every evaluation."""
+        key = (name, tuple(shape), np.dtype(dtype).str)
+        buf = self._pinned_bufs.get(key)
+        if buf is None:
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            ptr = C.c_void_p()
+            self._check(self.lib.cafe_b200_host_alloc(nbytes, C.byref(ptr)), "host_alloc")
+            raw = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+            buf = (np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape), ptr)
+            self._pinned_bufs[key] = buf
+        return buf[0]
+
+    def eval_gamma(self, lambdas, alpha, multipliers, cat_probs, want_family=True, pinned=False):
+        """pinned=True: the per-family outputs land in page-locked buffers owned by the context and overwritten by the next
+        pinned call (what a host that keeps its result vectors between evaluations does); default: fresh numpy arrays."""
         lam = _lib.as_f64(lambdas)
         mu = _lib.as_f64(multipliers)
         cp = _lib.as_f64(cat_probs)
@@ -153,7 +173,11 @@ class Context:
         neg = C.c_double()
         nf = C.c_int64()
         out = dict(cat_lk=None, family_lk=None, posterior=None, significant=None, failed=None)
-        if want_family:
+        if want_family and pinned:
+            out = dict(cat_lk=self._pinned("cat_lk", (self.F, K), np.float64), family_lk=self._pinned("family_lk", (self.F,), np.float64),
+                       posterior=self._pinned("posterior", (self.F, K), np.float64),
+                       significant=self._pinned("significant", (self.F, K), np.uint8), failed=self._pinned("failed", (self.F,), np.uint8))
+        elif want_family:
             out = dict(cat_lk=np.zeros((self.F, K)), family_lk=np.zeros(self.F), posterior=np.zeros((self.F, K)),
                        significant=np.zeros((self.F, K), dtype=np.uint8), failed=np.zeros(self.F, dtype=np.uint8))
         self._check(self.lib.cafe_b200_eval_gamma(self.h, _lib.dp(lam), len(lam), float(alpha), _lib.dp(mu), _lib.dp(cp), K,

@@ -30,6 +30,7 @@
 #ifndef CAFE_B200_H
 #define CAFE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -240,6 +241,13 @@ int cafe_b200_last_stats(cafe_b200_ctx* ctx, int32_t* n_launches, int32_t* n_mat
 /* FP64 pipe microbenchmark on `device` (register-resident DFMA chains, or mma.sync m8n8k4 DMMA tiles when
  * use_dmma != 0): the roofline denominator of the pruning kernel, measured on the GPU the bench runs on. */
 int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops);
+
+/* Page-locked host memory for the caller-owned input / output buffers of the calls above.  Any host pointer works; buffers
+ * obtained here are copied by the DMA engines directly (no staging copy, no page faults on a fresh allocation), which is what
+ * a host that keeps its result vectors between evaluations - like the reference's model::results (src/core.h:139) and
+ * gamma_model::_category_likelihoods (src/gamma_core.h:46) - should use.  Independent of any context. */
+int cafe_b200_host_alloc(size_t bytes, void** out);
+int cafe_b200_host_free(void* p);
 
 /* Number of distinct count vectors actually pruned (the reference list's unique entries). */
 int64_t cafe_b200_unique_families(const cafe_b200_ctx* ctx);
