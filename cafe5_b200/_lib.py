@@ -18,7 +18,7 @@ SYMBOLS = [
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
     "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit", "cafe_b200_simulate", "cafe_b200_pvalues", "cafe_b200_io_last_error", "cafe_b200_io_parse_tree", "cafe_b200_io_read_families",
     "cafe_b200_io_read_error_model", "cafe_b200_io_derive_sizes", "cafe_b200_io_format_results", "cafe_b200_io_format_family_likelihoods", "cafe_b200_io_format_reconstruction", "cafe_b200_branch_probabilities",
-    "cafe_b200_host_alloc", "cafe_b200_host_free",
+    "cafe_b200_host_alloc", "cafe_b200_host_free", "cafe_b200_debug_read_probe",
 ]
 
 c_dp = C.POINTER(C.c_double)
@@ -83,6 +83,7 @@ def load():
     L.cafe_b200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, c_dp]
     L.cafe_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.cafe_b200_host_free.argtypes = [C.c_void_p]
+    L.cafe_b200_debug_read_probe.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
     L.cafe_b200_describe.argtypes = [vp, C.POINTER(C.c_int64), c_ip, c_ip, c_ip, c_ip, c_dp]
     L.cafe_b200_discrete_gamma.argtypes = [C.c_int32, C.c_double, c_dp, c_dp]
     L.cafe_b200_minimize.argtypes = [OBJECTIVE, C.c_void_p, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, c_ip]

@@ -347,7 +347,12 @@ void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
     if (!c->use_dmma) CK(launch_prune_dfma(c->TM, c->TN, c->grid, c->S, c->stream, p));
     else if (c->prune_kind == 2) {
-        if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
+        if (c->WN == 2 && c->resident_probe) {
+            c->d_probe.reserve((size_t)2 * 4 * (PROBE_CHUNKS * 4 + 4));
+            CK(cudaMemsetAsync(c->d_probe.p, 0, c->d_probe.cap * sizeof(int64_t), c->stream));
+            p.probe = c->d_probe.p;
+            CK(launch_prune_resident_wn2probe(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
+        } else if (c->WN == 2) CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
         else CK(launch_prune_resident_wn4(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, p, c->sched));
     } else CK(launch_prune_stream(c->TM, c->TNW, c->grid, c->dmma_stages, c->stream, p));
 }
@@ -531,6 +536,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->smem_optin = prop.sharedMemPerBlockOptin;
         c->smem_per_sm = prop.sharedMemPerMultiprocessor;
         if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = v == 4 ? 4 : 2; }
+        if (const char* e = std::getenv("CAFE_B200_RESIDENT_PROBE")) c->resident_probe = std::atoi(e) != 0;
         if (const char* e = std::getenv("CAFE_B200_PUPKO_THREADS")) c->pupko_threads = std::atoi(e) == 256 ? 256 : 512;
         if (const char* e = std::getenv("CAFE_B200_MATGEN")) { c->matgen_entry = std::strcmp(e, "entry") == 0; c->matgen_libexp = std::strcmp(e, "rows") == 0; }
         if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
@@ -631,10 +637,10 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
     c->d_zero.release(); c->d_lg.release(); c->d_arena.release(); c->d_scratch.release(); c->d_prior.release(); c->d_logprior.release();
-    c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release(); c->d_powtab.release();
+    c->d_em.release(); c->d_best.release(); c->d_cat_probs.release(); c->d_ok.release(); c->d_params.release(); c->d_powtab.release(); c->d_probe.release();
     c->d_family_lnl.release(); c->d_cat_lk.release(); c->d_family_lk.release(); c->d_posterior.release();
     c->d_partial.release(); c->d_partial_fail.release(); c->d_result.release(); c->d_roots.release();
-    c->d_significant.release(); c->d_failed.release(); c->d_argmax.release(); c->d_states.release();
+    c->d_significant.release(); c->d_failed.release(); c->d_pupko_m.release(); c->d_states.release();
     c->d_leaf_row.release(); c->d_states_f.release(); c->d_cat_states_f.release(); c->d_avg_f.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
@@ -794,6 +800,20 @@ int cafe_b200_describe(const cafe_b200_ctx* c, int64_t* n_families, int32_t* n_n
     return CAFE_B200_OK;
 }
 
+int cafe_b200_debug_read_probe(cafe_b200_ctx* c, int64_t* out, int64_t n)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    try {
+        if (!out || n < 0) throw CudaError{"ARG: bad argument"};
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        const size_t m = std::min<size_t>((size_t)n, c->d_probe.cap);
+        if (m) CK(cudaMemcpy(out, c->d_probe.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        for (size_t i = m; i < (size_t)n; ++i) out[i] = 0;
+        return CAFE_B200_OK;
+    } catch (const CudaError& e) { return fail(c, e); }
+}
+
 int cafe_b200_host_alloc(size_t bytes, void** out)
 {
     try {
@@ -940,9 +960,9 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         c->d_scratch.reserve((size_t)c->grid * c->n_slots * p.slot_stride);
         p.scratch = c->d_scratch.p;
         p.n_steps = (int)c->steps.size();
-        p.arg_stride = (int64_t)c->n_mtiles * bm * bn;
-        c->d_argmax.reserve((size_t)c->grid * p.n_steps * p.arg_stride);
-        p.argmax = c->d_argmax.p;
+        p.m_stride = (int64_t)((c->S + PRUNE_BK - 1) / PRUNE_BK * PRUNE_BK) * bn;
+        c->d_pupko_m.reserve((size_t)c->grid * p.n_steps * p.m_stride);
+        p.mstore = c->d_pupko_m.p;
         c->d_states.reserve((size_t)K * c->U_stride * c->n_nodes);
         p.states = c->d_states.p;
         p.U = c->U; p.U_stride = c->U_stride;

@@ -115,13 +115,15 @@ struct cafe_b200_ctx {
     cafe::DevBuf<uint8_t> d_ok;
     cafe::DevBuf<cafe::MatParam> d_params;
     cafe::DevBuf<double> d_powtab;               // [N][n_mats] pow(coeff, j) of every key (pow_table_kernel)
+    bool resident_probe = false;                 // CAFE_B200_RESIDENT_PROBE=1: timing build with clock stamps (cafe_b200_debug_read_probe)
+    cafe::DevBuf<int64_t> d_probe;
     int pupko_threads = 512;                     // CAFE_B200_PUPKO_THREADS=256: the two-warps-per-sub-partition comparison geometry
     bool matgen_entry = false;                   // CAFE_B200_MATGEN=entry: the one-thread-per-entry comparison kernel
     bool matgen_libexp = false;                  // CAFE_B200_MATGEN=rows: the default kernel with the library exp() per term
     cafe::DevBuf<double> d_family_lnl, d_cat_lk, d_family_lk, d_posterior, d_partial, d_partial_fail, d_result, d_roots;
     cafe::DevBuf<uint8_t> d_significant, d_failed;
     // pupko
-    cafe::DevBuf<uint16_t> d_argmax;
+    cafe::DevBuf<double> d_pupko_m;              // [grid][n_steps][kpad * BN]: M_v of every node of the tiles in flight
     cafe::DevBuf<int32_t> d_states, d_leaf_row, d_states_f, d_cat_states_f;
     cafe::DevBuf<double> d_avg_f;
     int lg_n = 0;

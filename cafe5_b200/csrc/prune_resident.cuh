@@ -55,10 +55,22 @@ struct ResidentCfg {
 
 // MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  Co-resident CTAs drift out of phase on their own (starting
 // them half a step apart on purpose changed nothing measurable), so one CTA's leaf gathers / stores overlap the other's DMMA stream.
-template <int TMW, int TNW, int WN, int BK, int MINB>
+// VARIANT 2 is a timing build: clock stamps around the phases of the chunk loop (tools/gpu_probe_chunks.py), not used by the product.
+template <int TMW, int TNW, int WN, int BK, int MINB, int VARIANT = 0>
 __global__ void __launch_bounds__(64 * WN, MINB)
 prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__ InlineSchedule sched)
 {
+    constexpr bool PROBE = VARIANT == 2;
+    constexpr bool MID = WN == 2;           // ring refill from the middle of the chunk's DMMA stream (see the chunk loop)
+    int64_t* probe_out = nullptr;
+    int probe_n = 0;
+    if (PROBE && p.probe && (blockIdx.x % 148) == 0 && (threadIdx.x & 31) == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        probe_out = p.probe + ((size_t)(blockIdx.x / 148) * (blockDim.x / 32) + threadIdx.x / 32) * (PROBE_CHUNKS * 4 + 4);
+        probe_out[0] = smid;
+        probe_out += 4;
+    }
     using Cfg = ResidentCfg<TMW, TNW, WN, BK>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, THREADS = Cfg::THREADS;
     // Where warp 0 refills the ring: before its own chunk (one more chunk of lead, but it first waits for the slowest warp) or after it.
@@ -223,7 +235,10 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     for (int j = 0; j < TNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
                 for (int chunk = 0; chunk < n_chunks; ++chunk) {
                     if (PRODUCE_FIRST) produce_one();               // refill the stage the previous chunk released: NS-1 chunks of lead
+                    long long t_a = 0, t_b = 0, t_c = 0;
+                    if (PROBE) t_a = clock64();
                     mbar_wait(full_bar + c_stage, c_phase);
+                    if (PROBE) t_b = clock64();
                     const double* As = stages + (size_t)c_stage * Cfg::STAGE_DOUBLES;
                     const double* Bs = Vres + (size_t)chunk * BK * BNP;
 #pragma unroll
@@ -236,14 +251,28 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < TNW; ++j) b[j] = bp[(wn * 8 * TNW + j * 8 + g) ^ swz_q];
 #pragma unroll
-                        for (int i = 0; i < TMW; ++i)
+                        for (int i = 0; i < TMW; ++i) {
+                            // A warp's DMMAs issue exactly 16 cycles apart (ptxas: stall 15 + NOP) and it cannot catch up on time spent elsewhere,
+                            // so the ring refill sits INSIDE the DMMA stream rather than after it (59.6 -> 59.2 ms per launch; as a serial
+                            // tail the refill + cursor bookkeeping was 15 % of a warp's time, profiles/r01_probe_chunks.txt).  Probing the
+                            // next chunk's barrier from inside the stream as well lost time (60.1 ms), as did loading the fragments just in time.
+                            if (MID && k4 == BK / 4 - 1 && i == TMW / 2) produce_one();
 #pragma unroll
                             for (int j = 0; j < TNW; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        }
                     }
+                    if (PROBE) t_c = clock64();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty_bar + c_stage);
                     if (++c_stage == NS) { c_stage = 0; c_phase ^= 1u; }
-                    if (!PRODUCE_FIRST) produce_one();
+                    if (!PRODUCE_FIRST && !MID) produce_one();
+                    if (PROBE && probe_out && probe_n < PROBE_CHUNKS) {
+                        probe_out[probe_n * 4 + 0] = t_a;
+                        probe_out[probe_n * 4 + 1] = t_b;
+                        probe_out[probe_n * 4 + 2] = t_c;
+                        probe_out[probe_n * 4 + 3] = clock64();
+                        ++probe_n;
+                    }
                 }
                 // ---- 4. the factor stays in registers for the parent, or is parked once in a global slot ----
                 if (sp.dst_kind == 1) {

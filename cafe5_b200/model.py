@@ -92,6 +92,7 @@ class Context:
 
     def __init__(self, tree, counts, max_family_size, max_root_family_size, device=0):
         self.lib = _lib.load()
+        self._pinned_bufs = {}
         self.tree = tree
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         self.F, self.n_species = counts.shape

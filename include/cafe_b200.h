@@ -242,6 +242,10 @@ int cafe_b200_last_stats(cafe_b200_ctx* ctx, int32_t* n_launches, int32_t* n_mat
  * use_dmma != 0): the roofline denominator of the pruning kernel, measured on the GPU the bench runs on. */
 int cafe_b200_measure_fp64_peak(int32_t device, int32_t use_dmma, double* tflops);
 
+/* Development hook: clock stamps written by the timing build of the pruning kernel (CAFE_B200_RESIDENT_PROBE=1; see
+ * tools/gpu_probe_chunks.py).  Zeros when that build was not used. */
+int cafe_b200_debug_read_probe(cafe_b200_ctx* ctx, int64_t* out, int64_t n);
+
 /* Page-locked host memory for the caller-owned input / output buffers of the calls above.  Any host pointer works; buffers
  * obtained here are copied by the DMA engines directly (no staging copy, no page faults on a fresh allocation), which is what
  * a host that keeps its result vectors between evaluations - like the reference's model::results (src/core.h:139) and
