@@ -520,4 +520,106 @@ inline void write_clade_results(std::ostream& ost, const Tree& t, size_t n_famil
     }
 }
 
+// <Model>_report.cafe (operator<<(ostream&, const Report&), src/report.cpp:45-165; Report::compute_expansion :167-184;
+// gene_family2report :186-221; built by estimator::execute, src/execute.cpp:190-197).  lambdas: the fitted values (may be empty);
+// lambda_tree: write the tree's lambda indices, else the reference's dummy tree of 1s; branch_probs[F x n_nodes] (-1 = none): only
+// families that have branch probabilities get a line (Report::add_line_item :223-229).  The reference writes no line break between
+// the "'ID'\t'Newick'" header and the first family; neither do we.
+inline void write_report(std::ostream& ost, const Tree& t, const std::vector<double>& lambdas, bool lambda_tree,
+                         const std::vector<std::string>& ids, const int32_t* states, const double* pvalues, const double* branch_probs)
+{
+    const std::vector<int> ape = ape_ids(t);
+    const int n = t.n_nodes(), root = n - 1;
+    std::vector<std::vector<int>> kids(n);
+    for (int i = n - 1; i >= 0; --i) if (t.parent[i] >= 0) kids[t.parent[i]].push_back(i);
+    std::function<void(std::ostream&, int, const std::function<std::string(int)>&)> newick =
+        [&](std::ostream& o, int v, const std::function<std::string(int)>& text) {        // clade::write_newick, src/clade.cpp:206-223
+            if (!kids[v].empty()) {
+                o << '(';
+                for (size_t i = 0; i < kids[v].size(); ++i) { if (i) o << ','; newick(o, kids[v][i], text); }
+                o << ')';
+            }
+            o << text(v);
+        };
+    std::vector<int> prefix, stack{root};                                                  // clade::apply_prefix_order, src/clade.cpp:275-291
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        for (auto it = kids[v].rbegin(); it != kids[v].rend(); ++it) stack.push_back(*it);
+        prefix.push_back(v);
+    }
+    auto id_text = [&](int v) { return (t.is_leaf[v] ? t.name[v] : std::string()) + "<" + std::to_string(ape[v]) + ">"; };
+
+    ost << "Tree:";
+    newick(ost, root, [&](int v) { std::ostringstream o; o << (t.is_leaf[v] ? t.name[v] : std::string()) << ":" << t.branch_length[v]; return o.str(); });
+    ost << "\n";
+    if (!lambdas.empty()) {
+        ost << "Lambda:\t";
+        for (double l : lambdas) ost << l << "\t";
+    }
+    ost << "\n";
+    ost << "Lambda tree:\t";
+    newick(ost, root, [&](int v) { return lambda_tree ? std::to_string(t.lambda_class[v] + 1) : std::string("1"); });
+    ost << "\n";
+    ost << "# IDs of nodes:";
+    newick(ost, root, id_text);
+    ost << "\n";
+    ost << "# Output format for: ' Average Expansion', 'Expansions', 'No Change', 'Contractions', and 'Branch-specific P-values' = (node ID, node ID): ";
+    for (int v : prefix)
+        if (!t.is_leaf[v]) {
+            ost << "(";
+            for (size_t i = 0; i < kids[v].size(); ++i) ost << (i ? "," : "") << ape[kids[v][i]];
+            ost << ") ";
+        }
+    ost << "\n";
+
+    // Report::compute_expansion: per non-root node, over all families, the difference from the parent
+    const size_t F = ids.size();
+    std::vector<float> average(n, 0.0f);
+    std::vector<int> expanded(n, 0), same(n, 0), decreased(n, 0);
+    for (int v = 0; v < n; ++v) {
+        if (t.parent[v] < 0) continue;
+        int total = 0;
+        for (size_t f = 0; f < F; ++f) {
+            const int d = states[f * n + v] - states[f * n + t.parent[v]];
+            total += d;
+            expanded[v] += d > 0;
+            decreased[v] += d < 0;
+            same[v] += d == 0;
+        }
+        average[v] = float(total) / float(F);
+    }
+    if (n > 1) {
+        auto per_child = [&](const char* header, const std::function<float(int)>& value) {
+            ost << header;
+            for (int v : prefix)
+                if (!t.is_leaf[v]) {
+                    ost << "\t(";
+                    for (size_t i = 0; i < kids[v].size(); ++i) ost << (i ? "," : "") << value(kids[v][i]);
+                    ost << ")";
+                }
+            ost << "\n";
+        };
+        per_child("Average Expansion:", [&](int v) { return average[v]; });
+        per_child("Expansion :", [&](int v) { return (float)expanded[v]; });      // write_delta streams the counts as floats
+        per_child("Remain :", [&](int v) { return (float)same[v]; });
+        per_child("Decrease :", [&](int v) { return (float)decreased[v]; });
+    }
+    ost << "'ID'\t'Newick'";
+    for (size_t f = 0; f < F; ++f) {
+        bool any = false;
+        for (int v = 0; branch_probs != nullptr && v < n; ++v) any = any || branch_probs[f * n + v] >= 0;
+        if (!any) continue;
+        ost << ids[f] << "\t";
+        newick(ost, root, [&](int v) {
+            std::ostringstream o;
+            o << (t.is_leaf[v] ? t.name[v] : std::string()) << "_" << states[f * n + v] << ":" << t.branch_length[v];
+            return o.str();
+        });
+        ost << "\t" << pvalues[f] << "\t";
+        newick(ost, root, id_text);
+        ost << std::endl;
+    }
+}
+
 }  // namespace cafe_b200_host

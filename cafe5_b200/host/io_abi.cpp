@@ -150,4 +150,20 @@ int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbe
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
+int cafe_b200_io_format_report(const char* newick, const char* lambda_newick, const double* lambdas, int32_t n_lambda,
+                               const char* ids_tabbed, int64_t n_families, const int32_t* states, const double* pvalues,
+                               const double* branch_probs, char* out, int64_t out_cap)
+{
+    try {
+        if (!newick || !states || !pvalues) throw std::runtime_error("null argument");
+        const bool lambda_tree = lambda_newick && *lambda_newick;
+        const cafe_b200_host::Tree t = cafe_b200_host::parse_newick(newick, lambda_tree ? lambda_newick : "");
+        const std::vector<std::string> ids = ids_from(ids_tabbed, n_families);
+        std::ostringstream ost;
+        cafe_b200_host::write_report(ost, t, std::vector<double>(lambdas, lambdas + (lambdas ? n_lambda : 0)), lambda_tree, ids, states,
+                                     pvalues, branch_probs);
+        return put(ost.str(), out, out_cap);
+    } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
+}
+
 }  // extern "C"

@@ -96,3 +96,17 @@ def format_reconstruction(newick, ids, states, what, pvalues=None, threshold=0.0
                                                   {"count": 0, "change": 1, "asr": 2, "family_results": 3, "clade_results": 4,
                                                    "branch_probabilities": 5}[what], buf, len(buf)))
     return buf.value.decode()
+
+
+def format_report(newick, ids, states, pvalues, lambdas=(), lambda_newick=None, branch_probs=None):
+    """<Model>_report.cafe text (src/report.cpp) from the reconstructed states[F, n_nodes], the family p-values and, for the per-family
+    lines, branch_probs[F, n_nodes] from Context.branch_probabilities (-1 = none)."""
+    L = _lib.load()
+    st = np.ascontiguousarray(states, dtype=np.int32)
+    pv = _lib.as_f64(pvalues)
+    lam = _lib.as_f64(list(lambdas)) if len(lambdas) else None
+    bp = None if branch_probs is None else _lib.as_f64(branch_probs)
+    buf = C.create_string_buffer(64 * st.size + (1 << 16))
+    _check(L, L.cafe_b200_io_format_report(newick.encode(), (lambda_newick or "").encode(), _lib.dp(lam), 0 if lam is None else len(lam),
+                                          "\t".join(ids).encode(), len(ids), _lib.ip(st), _lib.dp(pv), _lib.dp(bp), buf, len(buf)))
+    return buf.value.decode()

@@ -208,6 +208,15 @@ int cafe_b200_io_format_reconstruction(const char* newick, const char* ids_tabbe
                                        const double* pvalues, double pvalue_threshold, const double* gamma_multipliers, int32_t n_cat,
                                        const double* branch_probs, int32_t what, char* out, int64_t out_cap);
 
+/* <Model>_report.cafe (operator<<(ostream&, const Report&), src/report.cpp:45-165, as estimator::execute builds it,
+ * src/execute.cpp:190-197): the tree, the fitted lambdas, the lambda tree (lambda_newick NULL / "": the reference's dummy tree of
+ * 1s), the ape node IDs, per-branch average expansion and expansion / no-change / contraction counts over all families, and one line
+ * (id, newick with reconstructed counts, p-value, newick with node IDs) per family that has branch probabilities
+ * (branch_probs[F x n_nodes] from cafe_b200_branch_probabilities, -1 = none; NULL: no family lines). */
+int cafe_b200_io_format_report(const char* newick, const char* lambda_newick, const double* lambdas, int32_t n_lambda,
+                               const char* ids_tabbed, int64_t n_families, const int32_t* states, const double* pvalues,
+                               const double* branch_probs, char* out, int64_t out_cap);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

@@ -440,6 +440,16 @@ class RefLib:
             self.ref._check(self.ref.lib.ref_branch_probabilities(self.h, _dp(lambdas), len(lambdas), _dp(pv), _dp(out), tab, asr, cap))
             return out, tab.value.decode(), asr.value.decode()
 
+        def write_report(self, lambdas, pvalues):
+            """<Model>_report.cafe text as the reference's estimator::execute builds it for the base model (src/execute.cpp:167-197)."""
+            lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+            pv = np.ascontiguousarray(pvalues, dtype=np.float64)
+            cap = 1 << 24
+            out = C.create_string_buffer(cap)
+            self.ref.lib.ref_write_report.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_char_p, C.c_long]
+            self.ref._check(self.ref.lib.ref_write_report(self.h, _dp(lambdas), len(lambdas), _dp(pv), out, cap))
+            return out.value.decode()
+
         def pvalues(self, lambdas, n_sims=1000, seed=1):
             """compute_pvalues of the unmodified reference (src/probability.cpp:528-570), randomizer_engine seeded with `seed`."""
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)

@@ -44,6 +44,7 @@
 #include "user_data.h"
 #include "io.h"
 #include "gene_family_reconstructor.h"
+#include "report.h"
 #include "optimizer.h"
 #include "newick_ape_loader.h"
 #include "optimizer_scorer.h"
@@ -474,6 +475,31 @@ int ref_branch_probabilities(void* h, const double* lambdas, int n_lambda, const
         rec->print_reconstructed_states(b, order, bp);
         if (put_text(a.str(), tab, cap) || put_text(b.str(), asr, cap)) return 1;
         return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// <Model>_report.cafe as estimator::execute builds it for the base model (src/execute.cpp:167-197): reconstruction, branch
+// probabilities for the families whose p-value is below ui.pvalue, Report::compute_expansion, one line item per family, operator<<.
+int ref_write_report(void* h, const double* lambdas, int n_lambda, const double* pvalues, char* out, long cap)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::unique_ptr<lambda> lam(make_lambda(c, lambdas, n_lambda));
+        matrix_cache cache(std::max(c->max_family_size, c->max_root_family_size) + 100);
+        cache.precalculate_matrices(get_lambda_values(lam.get()), c->tree->get_branch_lengths());
+        base_model m(lam.get(), c->tree.get(), &c->ud.gene_families, c->max_family_size, c->max_root_family_size, nullptr);
+        std::unique_ptr<reconstruction> rec(m.reconstruct_ancestral_states(c->ud, c->ui, &cache));
+        branch_probabilities bp;
+        for (size_t i = 0; i < c->ud.gene_families.size(); ++i)
+            if (pvalues[i] < c->ui.pvalue)
+                for (auto node : c->order)
+                    bp.set(c->ud.gene_families[i], node, compute_viterbi_sum(node, c->ud.gene_families[i], rec.get(), c->max_family_size, cache, lam.get()));
+        Report r(c->tree.get(), c->lambda_tree.get(), lam.get());
+        r.compute_expansion(c->ud.gene_families, *rec.get());
+        for (size_t i = 0; i < c->ud.gene_families.size(); ++i) r.add_line_item(c->ud.gene_families[i], rec.get(), pvalues[i], bp);
+        std::ostringstream ost;
+        ost << r;
+        return put_text(ost.str(), out, cap) ? 1 : 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 

@@ -201,3 +201,33 @@ def test_cpp_branch_probability_tables_reproduce_the_reference_text(ref):
     assert io_cpp.format_reconstruction(newick, ids, states, "branch_probabilities", branch_probs=probs) == tab_txt
     assert io_cpp.format_reconstruction(newick, ids, states, "asr", branch_probs=probs, threshold=0.05) == asr_txt
     assert "*" in asr_txt
+
+
+def test_cpp_report_reproduces_the_reference_text(ref):
+    """<Model>_report.cafe (src/report.cpp): the C++ writer fed with the reference's own reconstruction, p-values and branch
+    probabilities against the text the reference's Report streams, with and without a lambda tree, including the reference's missing
+    line break after the 'ID' / 'Newick' header."""
+    newick = "(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25)"
+    lambda_newick = "(((A:1,B:1):1,(C:1,D:1):1):1,(E:2,(F:2,G:2):2):2)"
+    rng = np.random.default_rng(5)
+    F = 12
+    mfs, mrs = 60, 45
+    ids = [str(i) for i in range(F)]
+    for lam_newick, lambdas in ((None, [0.0123]), (lambda_newick, [0.01, 0.03])):
+        tree = FlatTree(newick, lam_newick) if lam_newick else FlatTree(newick)
+        base = rng.integers(1, 20, size=F)
+        counts = np.clip(base[:, None] + rng.integers(-6, 7, size=(F, tree.n_leaves)), 0, 40).astype(np.int32)
+        pv = np.where(np.arange(F) % 3 == 0, 0.2, 0.0125)
+        rctx = ref.ctx(newick, tree.species, counts, mfs, mrs, fam.uniform_prior(mrs), lambda_newick=lam_newick)
+        want = rctx.write_report(lambdas, pv)
+        probs, _, _ = rctx.branch_probabilities(lambdas, pv)
+        states = rctx.reconstruct_base(lambdas)
+        rctx.close()
+        got = io_cpp.format_report(newick, ids, states, pv, lambdas=lambdas, lambda_newick=lam_newick, branch_probs=probs)
+        assert got == want
+        assert got.startswith("Tree:(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25):0\nLambda:\t")
+        assert "'ID'\t'Newick'1\t" in got                  # family 1 is the first with branch probabilities; no line break before it
+        assert got.count("\n") == 9 + int((pv < 0.05).sum())
+    # no branch probabilities at all: the header block only
+    head = io_cpp.format_report(newick, ids, states, pv, lambdas=[0.01, 0.03], lambda_newick=lambda_newick)
+    assert head.endswith("'ID'\t'Newick'") and head == want[:len(head)]
