@@ -36,6 +36,7 @@ texts = [io_cpp.format_results("Base", neg, lam, ctx.describe()["longest_branch"
          io_cpp.format_family_likelihoods(ids, "base", family_values=famlnl)]
 texts += [io_cpp.format_reconstruction(newick, ids, states, w, pvalues=pv, branch_probs=bp)
           for w in ("count", "change", "asr", "family_results", "clade_results", "branch_probabilities")]
+texts.append(io_cpp.format_report(newick, ids, states, pv, lambdas=lam, branch_probs=bp))      # Base_report.cafe
 out["tables_s"] = time.time() - t
 out["tables_bytes"] = sum(len(x) for x in texts)
 ctx.close()
