@@ -622,4 +622,26 @@ inline void write_report(std::ostream& ost, const Tree& t, const std::vector<dou
     }
 }
 
+// simulation.txt / simulation_truth.txt (simulator::print_simulations, src/simulator.cpp:135-172; simulator::simulate :97-132 writes
+// the leaf table and, with include_internal, the "truth" table whose interior columns are labelled with the node's position in the
+// reverse level order).  node_sizes[F x n_nodes] as cafe_b200_simulate returns them; family_lambda[f]: the first lambda of the
+// (perturbed / category) lambda family f was simulated with (simulated_family::lambda, create_trial :35).
+inline void write_simulations(std::ostream& ost, const Tree& t, size_t n_families, const int32_t* node_sizes, const double* family_lambda,
+                              bool include_internal)
+{
+    const int n = t.n_nodes();
+    ost << "DESC\tFID";
+    for (int i = 0; i < n; ++i) {
+        if (t.is_leaf[i]) ost << '\t' << t.name[i];
+        else if (include_internal) ost << '\t' << i;
+    }
+    ost << std::endl;
+    for (size_t f = 0; f < n_families; ++f) {
+        ost << "L" << family_lambda[f] << "\tsimfam" << f;
+        for (int i = 0; i < n; ++i)
+            if (t.is_leaf[i] || include_internal) ost << '\t' << node_sizes[f * n + i];
+        ost << std::endl;
+    }
+}
+
 }  // namespace cafe_b200_host

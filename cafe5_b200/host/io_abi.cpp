@@ -166,4 +166,16 @@ int cafe_b200_io_format_report(const char* newick, const char* lambda_newick, co
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
+int cafe_b200_io_format_simulation(const char* newick, int64_t n_families, const int32_t* node_sizes, const double* family_lambda,
+                                   int32_t include_internal, char* out, int64_t out_cap)
+{
+    try {
+        if (!newick || !node_sizes || !family_lambda || n_families < 0) throw std::runtime_error("bad argument");
+        const cafe_b200_host::Tree t = cafe_b200_host::parse_newick(newick);
+        std::ostringstream ost;
+        cafe_b200_host::write_simulations(ost, t, (size_t)n_families, node_sizes, family_lambda, include_internal != 0);
+        return put(ost.str(), out, out_cap);
+    } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
+}
+
 }  // extern "C"

@@ -110,3 +110,14 @@ def format_report(newick, ids, states, pvalues, lambdas=(), lambda_newick=None, 
     _check(L, L.cafe_b200_io_format_report(newick.encode(), (lambda_newick or "").encode(), _lib.dp(lam), 0 if lam is None else len(lam),
                                           "\t".join(ids).encode(), len(ids), _lib.ip(st), _lib.dp(pv), _lib.dp(bp), buf, len(buf)))
     return buf.value.decode()
+
+
+def format_simulation(newick, node_sizes, family_lambda, include_internal=False):
+    """simulation.txt / simulation_truth.txt text (src/simulator.cpp:135-172) from node_sizes[F, n_nodes] of Context.simulate and the
+    lambda each family was simulated with."""
+    L = _lib.load()
+    ns = np.ascontiguousarray(node_sizes, dtype=np.int32)
+    fl = _lib.as_f64(family_lambda)
+    buf = C.create_string_buffer(16 * ns.size + 64 * ns.shape[0] + (1 << 16))
+    _check(L, L.cafe_b200_io_format_simulation(newick.encode(), ns.shape[0], _lib.ip(ns), _lib.dp(fl), int(bool(include_internal)), buf, len(buf)))
+    return buf.value.decode()

@@ -217,6 +217,12 @@ int cafe_b200_io_format_report(const char* newick, const char* lambda_newick, co
                                const char* ids_tabbed, int64_t n_families, const int32_t* states, const double* pvalues,
                                const double* branch_probs, char* out, int64_t out_cap);
 
+/* simulation.txt (include_internal = 0) / simulation_truth.txt (include_internal != 0) as simulator::print_simulations writes them
+ * (src/simulator.cpp:135-172) from node_sizes[F x n_nodes] of cafe_b200_simulate (nodes in the order cafe_b200_io_parse_tree gives for
+ * `newick`) and the lambda each family was simulated with (family_lambda[F]: first lambda x the family's multiplier). */
+int cafe_b200_io_format_simulation(const char* newick, int64_t n_families, const int32_t* node_sizes, const double* family_lambda,
+                                   int32_t include_internal, char* out, int64_t out_cap);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

@@ -440,6 +440,16 @@ class RefLib:
             self.ref._check(self.ref.lib.ref_branch_probabilities(self.h, _dp(lambdas), len(lambdas), _dp(pv), _dp(out), tab, asr, cap))
             return out, tab.value.decode(), asr.value.decode()
 
+        def print_simulations(self, node_sizes, family_lambda, include_internal):
+            """simulation.txt / simulation_truth.txt text of the reference's simulator::print_simulations for the given node values."""
+            ns = np.ascontiguousarray(node_sizes, dtype=np.int32)
+            fl = np.ascontiguousarray(family_lambda, dtype=np.float64)
+            cap = 1 << 24
+            out = C.create_string_buffer(cap)
+            self.ref.lib.ref_print_simulations.argtypes = [C.c_void_p, C.c_long, c_ip, c_dp, C.c_int, C.c_char_p, C.c_long]
+            self.ref._check(self.ref.lib.ref_print_simulations(self.h, ns.shape[0], _ip(ns), _dp(fl), int(bool(include_internal)), out, cap))
+            return out.value.decode()
+
         def write_report(self, lambdas, pvalues):
             """<Model>_report.cafe text as the reference's estimator::execute builds it for the base model (src/execute.cpp:167-197)."""
             lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)

@@ -45,6 +45,7 @@
 #include "io.h"
 #include "gene_family_reconstructor.h"
 #include "report.h"
+#include "simulator.h"
 #include "optimizer.h"
 #include "newick_ape_loader.h"
 #include "optimizer_scorer.h"
@@ -499,6 +500,25 @@ int ref_write_report(void* h, const double* lambdas, int n_lambda, const double*
         for (size_t i = 0; i < c->ud.gene_families.size(); ++i) r.add_line_item(c->ud.gene_families[i], rec.get(), pvalues[i], bp);
         std::ostringstream ost;
         ost << r;
+        return put_text(ost.str(), out, cap) ? 1 : 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// simulation.txt / simulation_truth.txt as simulator::print_simulations writes them (src/simulator.cpp:135-172) for n families whose
+// node values (n x n_nodes, reverse level order) and lambdas are given.
+int ref_print_simulations(void* h, long n, const int* node_sizes, const double* lambdas, int include_internal, char* out, long cap)
+{
+    auto c = (ref_ctx*)h;
+    try {
+        std::vector<simulated_family> results(n);
+        const size_t nn = c->order.size();
+        for (long f = 0; f < n; ++f) {
+            results[f].lambda = lambdas[f];
+            for (size_t k = 0; k < nn; ++k) results[f].values[c->order[k]] = node_sizes[f * nn + k];
+        }
+        simulator sim(c->ud, c->ui);
+        std::ostringstream ost;
+        sim.print_simulations(ost, include_internal != 0, results);
         return put_text(ost.str(), out, cap) ? 1 : 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -231,3 +231,23 @@ def test_cpp_report_reproduces_the_reference_text(ref):
     # no branch probabilities at all: the header block only
     head = io_cpp.format_report(newick, ids, states, pv, lambdas=[0.01, 0.03], lambda_newick=lambda_newick)
     assert head.endswith("'ID'\t'Newick'") and head == want[:len(head)]
+
+
+def test_cpp_simulation_tables_reproduce_the_reference_text(ref):
+    """simulation.txt and simulation_truth.txt (simulator::print_simulations, src/simulator.cpp:135-172): the C++ writer against the
+    reference's own printer on the same node values, leaves only and with the interior columns."""
+    newick = "(((A:1.25,B:1.25):2,(C:2,D:2):1.25):3,(E:5,(F:0.5,G:0.5):4.5):1.25)"
+    tree = FlatTree(newick)
+    rng = np.random.default_rng(6)
+    F = 9
+    sizes = rng.integers(0, 60, size=(F, tree.n_nodes)).astype(np.int32)
+    lambdas = 0.0123 * rng.choice([0.062015465425384449, 0.37328920830134099, 0.99805780528212318, 2.5666375209911516], size=F)
+    counts = np.ones((1, tree.n_leaves), dtype=np.int32)
+    rctx = ref.ctx(newick, tree.species, counts, 60, 45, fam.uniform_prior(45))
+    for internal in (False, True):
+        want = rctx.print_simulations(sizes, lambdas, internal)
+        got = io_cpp.format_simulation(newick, sizes, lambdas, include_internal=internal)
+        assert got == want
+        assert got.startswith("DESC\tFID\t") and got.count("\n") == F + 1
+        assert ("\t%d\t" % (tree.n_nodes - 1) in got.splitlines()[0] + "\t") == internal       # the root's column exists only in the truth table
+    rctx.close()
