@@ -18,7 +18,7 @@ SYMBOLS = [
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
     "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit", "cafe_b200_simulate", "cafe_b200_pvalues", "cafe_b200_io_last_error", "cafe_b200_io_parse_tree", "cafe_b200_io_read_families",
     "cafe_b200_io_read_error_model", "cafe_b200_io_derive_sizes", "cafe_b200_io_format_results", "cafe_b200_io_format_family_likelihoods", "cafe_b200_io_format_reconstruction", "cafe_b200_branch_probabilities",
-    "cafe_b200_host_alloc", "cafe_b200_host_free", "cafe_b200_debug_read_probe", "cafe_b200_io_format_report", "cafe_b200_io_format_simulation",
+    "cafe_b200_host_alloc", "cafe_b200_host_free", "cafe_b200_debug_read_probe", "cafe_b200_io_format_report", "cafe_b200_io_format_simulation", "cafe_b200_io_format_error_model",
 ]
 
 c_dp = C.POINTER(C.c_double)
@@ -103,6 +103,7 @@ def load():
     L.cafe_b200_io_format_reconstruction.argtypes = [cs, cs, C.c_int64, c_ip, c_dp, C.c_double, c_dp, C.c_int32, c_dp, C.c_int32, C.c_char_p, C.c_int64]
     L.cafe_b200_io_format_report.argtypes = [cs, cs, c_dp, C.c_int32, cs, C.c_int64, c_ip, c_dp, c_dp, C.c_char_p, C.c_int64]
     L.cafe_b200_io_format_simulation.argtypes = [cs, C.c_int64, c_ip, c_dp, C.c_int32, C.c_char_p, C.c_int64]
+    L.cafe_b200_io_format_error_model.argtypes = [c_dp, C.c_int32, C.c_char_p, C.c_int64]
     L.cafe_b200_branch_probabilities.argtypes = [vp, c_dp, C.c_int32, c_ip, c_up, c_dp]
     _lib = L
     return L

@@ -644,4 +644,20 @@ inline void write_simulations(std::ostream& ost, const Tree& t, size_t n_familie
     }
 }
 
+// The error model file the reference writes after estimating epsilon (write_error_model_file, src/io.cpp:277-297; called from
+// src/execute.cpp:37 and src/core.cpp:127): "maxcnt" = the number of table rows - 1 (error_model::get_max_family_size returns the table
+// size, src/error_model.h:55-57), the deviations, then one line per family size whose probabilities differ from the previous size's.
+inline void write_error_model(std::ostream& ost, const ErrorModelTable& em)
+{
+    ost << "maxcnt: " << em.rows() - 1 << "\n";
+    ost << "cntdiff: -1 0 1\n";
+    const double* last = nullptr;
+    for (int j = 0; j < em.rows(); ++j) {
+        const double* row = em.probs.data() + 3 * (size_t)j;
+        if (last != nullptr && row[0] == last[0] && row[1] == last[1] && row[2] == last[2]) continue;
+        last = row;
+        ost << j << " " << row[0] << " " << row[1] << " " << row[2] << std::endl;
+    }
+}
+
 }  // namespace cafe_b200_host

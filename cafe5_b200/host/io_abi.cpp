@@ -178,4 +178,16 @@ int cafe_b200_io_format_simulation(const char* newick, int64_t n_families, const
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
+int cafe_b200_io_format_error_model(const double* probs, int32_t rows, char* out, int64_t out_cap)
+{
+    try {
+        if (!probs || rows <= 0) throw std::runtime_error("bad argument");
+        cafe_b200_host::ErrorModelTable em;
+        em.probs.assign(probs, probs + 3 * (size_t)rows);
+        std::ostringstream ost;
+        cafe_b200_host::write_error_model(ost, em);
+        return put(ost.str(), out, out_cap);
+    } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
+}
+
 }  // extern "C"

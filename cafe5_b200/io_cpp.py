@@ -121,3 +121,12 @@ def format_simulation(newick, node_sizes, family_lambda, include_internal=False)
     buf = C.create_string_buffer(16 * ns.size + 64 * ns.shape[0] + (1 << 16))
     _check(L, L.cafe_b200_io_format_simulation(newick.encode(), ns.shape[0], _lib.ip(ns), _lib.dp(fl), int(bool(include_internal)), buf, len(buf)))
     return buf.value.decode()
+
+
+def format_error_model(probs):
+    """Error model file text (write_error_model_file, src/io.cpp:277-297) from probs[rows, 3]."""
+    L = _lib.load()
+    pr = np.ascontiguousarray(probs, dtype=np.float64).reshape(-1, 3)
+    buf = C.create_string_buffer(96 * pr.shape[0] + (1 << 12))
+    _check(L, L.cafe_b200_io_format_error_model(_lib.dp(pr), pr.shape[0], buf, len(buf)))
+    return buf.value.decode()

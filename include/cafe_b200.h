@@ -223,6 +223,10 @@ int cafe_b200_io_format_report(const char* newick, const char* lambda_newick, co
 int cafe_b200_io_format_simulation(const char* newick, int64_t n_families, const int32_t* node_sizes, const double* family_lambda,
                                    int32_t include_internal, char* out, int64_t out_cap);
 
+/* The error model file the reference writes once epsilon has been estimated (write_error_model_file, src/io.cpp:277-297): probs
+ * [rows x 3] as cafe_b200_io_read_error_model returns them / as cafe_b200_set_error_model takes them ("maxcnt" is rows - 1). */
+int cafe_b200_io_format_error_model(const double* probs, int32_t rows, char* out, int64_t out_cap);
+
 /* Test hooks ------------------------------------------------------------------------------- */
 
 /* matrix_cache::get_matrix (src/matrix_cache.cpp:88-105) for one (lambda, branch length) key after

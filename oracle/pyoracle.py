@@ -489,6 +489,15 @@ class RefLib:
     def ctx(self, *a, **k):
         return RefLib.Ctx(self, *a, **k)
 
+    def write_error_model(self, probs, max_count):
+        """Error model file text of the reference's write_error_model_file for probs[rows, 3] and max_count."""
+        pr = np.ascontiguousarray(probs, dtype=np.float64).reshape(-1, 3)
+        cap = 1 << 20
+        out = C.create_string_buffer(cap)
+        self.lib.ref_write_error_model.argtypes = [c_dp, C.c_int, C.c_int, C.c_char_p, C.c_long]
+        self._check(self.lib.ref_write_error_model(_dp(pr), pr.shape[0], int(max_count), out, cap))
+        return out.value.decode()
+
     # timing legs for bench.py (see oracle/ref_driver.cpp)
     def time_precalculate(self, ctx, lambdas, multipliers, stride):
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)

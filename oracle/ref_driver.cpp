@@ -504,6 +504,22 @@ int ref_write_report(void* h, const double* lambdas, int n_lambda, const double*
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// The error model file as the reference writes it (write_error_model_file, src/io.cpp:277-297) for a model built like ref_ctx_create
+// builds it (set_max_family_size, set_deviations, set_probabilities).
+int ref_write_error_model(const double* em_probs, int em_rows, int em_maxcnt, char* out, long cap)
+{
+    ensure_init();
+    try {
+        error_model em;
+        em.set_max_family_size(em_maxcnt);
+        em.set_deviations({"-1", "0", "1"});
+        for (int i = 0; i < em_rows; ++i) em.set_probabilities(i, {em_probs[3 * i], em_probs[3 * i + 1], em_probs[3 * i + 2]});
+        std::ostringstream ost;
+        write_error_model_file(ost, em);
+        return put_text(ost.str(), out, cap) ? 1 : 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
 // simulation.txt / simulation_truth.txt as simulator::print_simulations writes them (src/simulator.cpp:135-172) for n families whose
 // node values (n x n_nodes, reverse level order) and lambdas are given.
 int ref_print_simulations(void* h, long n, const int* node_sizes, const double* lambdas, int include_internal, char* out, long cap)

@@ -251,3 +251,19 @@ def test_cpp_simulation_tables_reproduce_the_reference_text(ref):
         assert got.startswith("DESC\tFID\t") and got.count("\n") == F + 1
         assert ("\t%d\t" % (tree.n_nodes - 1) in got.splitlines()[0] + "\t") == internal       # the root's column exists only in the truth table
     rctx.close()
+
+
+def test_cpp_error_model_writer_reproduces_the_reference_text(ref):
+    """The error model file written after epsilon has been estimated (write_error_model_file, src/io.cpp:277-297): one line per size
+    whose probabilities differ from the previous size's; "maxcnt" is the number of table rows - 1 whatever the model's size limit."""
+    for eps, rows, max_count in ((0.1, 91, 91), (0.0417, 3, 60), (0.25, 1, 10)):
+        probs = np.tile([eps, 1 - 2 * eps, eps], (rows, 1))
+        probs[0] = [0.0, 1 - eps, eps]
+        want = ref.write_error_model(probs, max_count)
+        got = io_cpp.format_error_model(probs)
+        assert got == want
+        assert got.startswith("maxcnt: %d\ncntdiff: -1 0 1\n0 0 " % (rows - 1))
+    # the reference's own example file round-trips through its reader and both writers
+    path = os.path.join(REF, "examples", "errormodel_0.1.txt")
+    em = io_cpp.read_error_model(path)
+    assert io_cpp.format_error_model(em[0]) == ref.write_error_model(em[0], em[1])
