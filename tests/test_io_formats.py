@@ -268,3 +268,24 @@ def test_cpp_error_model_writer_reproduces_the_reference_text(ref):
     if os.path.exists(path):                                  # the reference's files are not present on the GPU box
         em = io_cpp.read_error_model(path)
         assert io_cpp.format_error_model(em[0]) == ref.write_error_model(em[0], em[1])
+
+
+def test_cpp_report_on_a_multifurcating_tree(ref):
+    """The report lists the children of every interior node: a node with three children gets a three-entry tuple in every block."""
+    newick = "((A:1,B:1,C:1):2,(D:1.5,E:1.5):1.5)"
+    tree = FlatTree(newick)
+    rng = np.random.default_rng(8)
+    F = 7
+    counts = rng.integers(0, 12, size=(F, tree.n_leaves)).astype(np.int32)
+    counts[:, 0] = np.maximum(counts[:, 0], 1)
+    counts[:, 3] = np.maximum(counts[:, 3], 1)
+    pv = np.full(F, 0.01)
+    ids = [str(i) for i in range(F)]
+    rctx = ref.ctx(newick, tree.species, counts, 40, 30, fam.uniform_prior(30))
+    want = rctx.write_report([0.02], pv)
+    probs, _, _ = rctx.branch_probabilities([0.02], pv)
+    states = rctx.reconstruct_base([0.02])
+    rctx.close()
+    got = io_cpp.format_report(newick, ids, states, pv, lambdas=[0.02], branch_probs=probs)
+    assert got == want
+    assert "(1,2,3) " in got.splitlines()[4]
