@@ -13,6 +13,12 @@ int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda
                        int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) {   // the simulator needs the tree and the matrices only: first device
+        const int rc = cafe_b200_simulate(c->shards[0], lambdas, n_lambda, multipliers, cat_probs, n_cat, max_sim, max_redraws, root_sizes,
+                                          n_families, seed, counts, node_sizes, categories, n_not_at_root);
+        if (rc != CAFE_B200_OK) c->err = c->shards[0]->err;
+        return rc;
+    }
     try {
         if (!lambdas || n_lambda < c->n_lambda_classes || !root_sizes || n_families <= 0 || !counts) throw CudaError{"ARG: bad argument"};
         if (n_cat > 0 && (!multipliers || !cat_probs)) throw CudaError{"ARG: gamma simulation needs multipliers and cat_probs"};
@@ -79,6 +85,16 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int3
                                    const uint8_t* selected, double* probs)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) {
+        if (!states || !probs) { c->err = "bad argument"; return CAFE_B200_ERR_ARG; }
+        int bad = -1;
+        const int rc = c->pool->run([&](int i) {
+            const size_t b = (size_t)c->shard_begin[i], nn = (size_t)c->n_nodes;
+            return cafe_b200_branch_probabilities(c->shards[i], lambdas, n_lambda, states + b * nn, selected ? selected + b : nullptr, probs + b * nn);
+        }, &bad);
+        if (rc != CAFE_B200_OK) c->err = c->shards[bad]->err;
+        return rc;
+    }
     try {
         if (!lambdas || n_lambda < c->n_lambda_classes || !states || !probs) throw CudaError{"ARG: bad argument"};
         CK(cudaSetDevice(c->device));
@@ -115,6 +131,13 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int3
 int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) {   // every device simulates the same conditional distributions (same seed) and scores its own shard of families
+        if (!pvalues) { c->err = "bad argument"; return CAFE_B200_ERR_ARG; }
+        int bad = -1;
+        const int rc = c->pool->run([&](int i) { return cafe_b200_pvalues(c->shards[i], lambdas, n_lambda, n_sims, seed, pvalues + c->shard_begin[i]); }, &bad);
+        if (rc != CAFE_B200_OK) c->err = c->shards[bad]->err;
+        return rc;
+    }
     cafe_b200_ctx* sim = nullptr;
     try {
         if (!lambdas || n_lambda < c->n_lambda_classes || n_sims < 1 || !pvalues) throw CudaError{"ARG: bad argument"};

@@ -492,6 +492,23 @@ namespace {
 
 }  // namespace
 
+// ---- cafe_b200_create_multi: a group context forwards every call to its device shards (defined at the end of this file) ----
+namespace group {
+int set_prior(cafe_b200_ctx* g, const float* prior, int32_t n);
+int set_error_model(cafe_b200_ctx* g, const double* probs, int32_t rows, int32_t max_cnt);
+int eval_base(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double* neg_lnl, double* family_lnl);
+int eval_gamma(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
+               int32_t n_cat, double* neg_lnl, double* cat_lk, double* family_lk, double* posterior, uint8_t* significant, uint8_t* failed,
+               int64_t* n_failed);
+int enqueue_eval(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
+                 int32_t n_cat);
+int fetch_result(cafe_b200_ctx* g, double* neg_lnl, int64_t* n_failed);
+int last_stats(cafe_b200_ctx* g, int32_t* n_launches, int32_t* n_matrices, float* ms_matrices, float* ms_prune);
+int root_vectors(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double multiplier, double* out);
+int reconstruct(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs, int32_t n_cat,
+                int32_t* cat_states, int32_t* states, double* averaged);
+}  // namespace group
+
 // ================================================================================================
 extern "C" {
 
@@ -633,6 +650,12 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
 int cafe_b200_destroy(cafe_b200_ctx* c)
 {
     if (!c) return CAFE_B200_OK;
+    if (c->is_group()) {
+        delete c->pool;
+        for (cafe_b200_ctx* s : c->shards) if (s) cafe_b200_destroy(s);
+        delete c;
+        return CAFE_B200_OK;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_counts_t.release(); c->d_mat_of.release(); c->d_gemm_nodes.release(); c->d_f2u.release(); c->d_steps.release(); c->d_children.release();
@@ -655,6 +678,7 @@ const char* cafe_b200_last_error(const cafe_b200_ctx* c) { return c ? c->err.c_s
 int cafe_b200_set_prior(cafe_b200_ctx* c, const float* prior, int32_t n)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::set_prior(c, prior, n);
     try {
         if (!prior || n < 0) throw CudaError{"ARG: null prior"};
         CK(cudaSetDevice(c->device));
@@ -680,6 +704,7 @@ int cafe_b200_set_prior(cafe_b200_ctx* c, const float* prior, int32_t n)
 int cafe_b200_set_error_model(cafe_b200_ctx* c, const double* probs, int32_t rows, int32_t max_cnt)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::set_error_model(c, probs, rows, max_cnt);
     try {
         CK(cudaSetDevice(c->device));
         if (!probs) { c->have_em = false; return CAFE_B200_OK; }
@@ -697,6 +722,7 @@ int cafe_b200_set_error_model(cafe_b200_ctx* c, const double* probs, int32_t row
 int cafe_b200_eval_base(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double* neg_lnl, double* family_lnl)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::eval_base(c, lambdas, n_lambda, neg_lnl, family_lnl);
     try {
         if (!lambdas || n_lambda < 1 || !neg_lnl) throw CudaError{"ARG: null argument"};
         CK(cudaSetDevice(c->device));
@@ -718,6 +744,7 @@ int cafe_b200_eval_gamma(cafe_b200_ctx* c, const double* lambdas, int32_t n_lamb
                          uint8_t* significant, uint8_t* failed, int64_t* n_failed)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::eval_gamma(c, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, neg_lnl, cat_lk, family_lk, posterior, significant, failed, n_failed);
     try {
         if (!lambdas || n_lambda < 1 || !neg_lnl || !multipliers || !cat_probs || n_cat < 1) throw CudaError{"ARG: null argument"};
         CK(cudaSetDevice(c->device));
@@ -744,6 +771,7 @@ int cafe_b200_enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int32_t n_la
                            const double* multipliers, const double* cat_probs, int32_t n_cat)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::enqueue_eval(c, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat);
     try {
         CK(cudaSetDevice(c->device));
         if (!enqueue_eval(c, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat))
@@ -755,6 +783,7 @@ int cafe_b200_enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int32_t n_la
 int cafe_b200_fetch_result(cafe_b200_ctx* c, double* neg_lnl, int64_t* n_failed)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::fetch_result(c, neg_lnl, n_failed);
     try {
         CK(cudaSetDevice(c->device));
         d2h(c, c->h_result, c->d_result.p, 2);
@@ -765,11 +794,12 @@ int cafe_b200_fetch_result(cafe_b200_ctx* c, double* neg_lnl, int64_t* n_failed)
     } catch (const CudaError& e) { return fail(c, e); }
 }
 
-void* cafe_b200_stream(cafe_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* cafe_b200_stream(cafe_b200_ctx* c) { return !c ? nullptr : c->is_group() ? (void*)c->shards[0]->stream : (void*)c->stream; }
 
 int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matrices, float* ms_matrices, float* ms_prune)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::last_stats(c, n_launches, n_matrices, ms_matrices, ms_prune);
     try {
         if (!c->stats_valid) throw CudaError{"STATE: no evaluation has been launched"};
         CK(cudaSetDevice(c->device));
@@ -785,7 +815,16 @@ int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matri
     } catch (const CudaError& e) { return fail(c, e); }
 }
 
-int64_t cafe_b200_unique_families(const cafe_b200_ctx* c) { return c ? c->U : 0; }
+int64_t cafe_b200_unique_families(const cafe_b200_ctx* c)
+{
+    if (!c) return 0;
+    if (!c->is_group()) return c->U;
+    int64_t u = 0;
+    for (const cafe_b200_ctx* s : c->shards) u += s->U;   // identical families in different shards are pruned once per shard
+    return u;
+}
+
+int32_t cafe_b200_n_devices(const cafe_b200_ctx* c) { return !c ? 0 : c->is_group() ? (int32_t)c->shards.size() : 1; }
 
 int cafe_b200_describe(const cafe_b200_ctx* c, int64_t* n_families, int32_t* n_nodes, int32_t* n_lambda_classes,
                        int32_t* max_family_size, int32_t* max_root_family_size, double* longest_branch)
@@ -803,6 +842,7 @@ int cafe_b200_describe(const cafe_b200_ctx* c, int64_t* n_families, int32_t* n_n
 int cafe_b200_debug_read_probe(cafe_b200_ctx* c, int64_t* out, int64_t n)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return cafe_b200_debug_read_probe(c->shards[0], out, n);
     try {
         if (!out || n < 0) throw CudaError{"ARG: bad argument"};
         CK(cudaSetDevice(c->device));
@@ -883,6 +923,7 @@ int32_t cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->N : 0; }
 int cafe_b200_get_matrix(cafe_b200_ctx* c, double lambda, double branch_length, double* out)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return cafe_b200_get_matrix(c->shards[0], lambda, branch_length, out);
     try {
         if (!out) throw CudaError{"ARG: null output"};
         CK(cudaSetDevice(c->device));
@@ -910,6 +951,7 @@ int cafe_b200_get_matrix(cafe_b200_ctx* c, double lambda, double branch_length, 
 int cafe_b200_root_vectors(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, double multiplier, double* out)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::root_vectors(c, lambdas, n_lambda, multiplier, out);
     try {
         if (!lambdas || !out || n_lambda < c->n_lambda_classes) throw CudaError{"ARG: bad argument"};
         if (!c->have_prior) throw CudaError{"STATE: set_prior must be called before eval"};
@@ -935,6 +977,7 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
                           int32_t* cat_states, int32_t* states, double* averaged)
 {
     if (!c) return CAFE_B200_ERR_ARG;
+    if (c->is_group()) return group::reconstruct(c, lambdas, n_lambda, multipliers, cat_probs, n_cat, cat_states, states, averaged);
     try {
         if (!lambdas || n_lambda < c->n_lambda_classes || !states) throw CudaError{"ARG: bad argument"};
         if (n_cat > 0 && (!multipliers || !cat_probs)) throw CudaError{"ARG: gamma reconstruction needs multipliers and cat_probs"};
@@ -996,3 +1039,167 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// cafe_b200_create_multi: families sharded contiguously over the devices of one node.  Every group call runs the
+// single-device entry point of all shards at once on the shard workers; per-family outputs land in the caller's buffers at the
+// shard's offset; the scalar partials are added on the host in shard order.
+extern "C" int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                                      int32_t max_family_size, int32_t max_root_family_size, const int32_t* devices, int32_t n_devices,
+                                      cafe_b200_ctx** out)
+{
+    if (out) *out = nullptr;
+    if (!devices || n_devices < 1 || !out) { create_error() = "null device list"; return CAFE_B200_ERR_ARG; }
+    if (n_devices == 1) return cafe_b200_create(tree, counts, n_families, n_species, max_family_size, max_root_family_size, devices[0], out);
+    if (!tree || !counts || n_families <= 0 || n_species <= 0) { create_error() = "null or non-positive argument"; return CAFE_B200_ERR_ARG; }
+    const int n_shards = (int)std::min<int64_t>(n_devices, n_families);
+    cafe_b200_ctx* g = new cafe_b200_ctx();
+    g->shards.assign(n_shards, nullptr);
+    g->shard_begin.resize(n_shards + 1);
+    for (int i = 0; i <= n_shards; ++i) g->shard_begin[i] = n_families * i / n_shards;
+    g->pool = new ShardPool(n_shards);
+    std::vector<std::string> errs(n_shards);
+    int bad = -1;
+    const int rc = g->pool->run([&](int i) {
+        const int64_t b = g->shard_begin[i], e = g->shard_begin[i + 1];
+        const int r = cafe_b200_create(tree, counts + (size_t)b * n_species, e - b, n_species, max_family_size, max_root_family_size,
+                                       devices[i], &g->shards[i]);
+        if (r != CAFE_B200_OK) errs[i] = cafe_b200_last_error(nullptr);   // create's error text is per thread
+        return r;
+    }, &bad);
+    if (rc != CAFE_B200_OK) {
+        create_error() = "device " + std::to_string(devices[bad]) + ": " + errs[bad];
+        cafe_b200_destroy(g);
+        return rc;
+    }
+    const cafe_b200_ctx* s0 = g->shards[0];
+    g->device = s0->device;
+    g->F = n_families;
+    g->n_species = n_species;
+    g->n_nodes = s0->n_nodes;
+    g->n_lambda_classes = s0->n_lambda_classes;
+    g->max_family_size = s0->max_family_size;
+    g->S = s0->S; g->R = s0->R; g->N = s0->N;
+    g->branch_length = s0->branch_length;
+    g->parent = s0->parent; g->leaf_col = s0->leaf_col; g->lambda_class = s0->lambda_class;
+    *out = g;
+    return CAFE_B200_OK;
+}
+
+namespace group {
+
+// run fn on every shard; on failure the group's error text is the failing shard's
+int each(cafe_b200_ctx* g, const std::function<int(int, cafe_b200_ctx*)>& fn)
+{
+    int bad = -1;
+    const int rc = g->pool->run([&](int i) { return fn(i, g->shards[i]); }, &bad);
+    if (rc != CAFE_B200_OK) g->err = "device " + std::to_string(g->shards[bad]->device) + ": " + g->shards[bad]->err;
+    return rc;
+}
+
+// -sum over families, shards added in device order (base_model.cpp:95, gamma_core.cpp:233); +inf when any shard rejected
+double combine(const std::vector<double>& neg)
+{
+    double total = 0.0;
+    for (double v : neg) total += v;
+    return total;
+}
+
+int set_prior(cafe_b200_ctx* g, const float* prior, int32_t n)
+{
+    const int rc = each(g, [&](int, cafe_b200_ctx* s) { return cafe_b200_set_prior(s, prior, n); });
+    if (rc == CAFE_B200_OK) { g->prior.assign(prior, prior + n); g->have_prior = true; }
+    return rc;
+}
+
+int set_error_model(cafe_b200_ctx* g, const double* probs, int32_t rows, int32_t max_cnt)
+{
+    const int rc = each(g, [&](int, cafe_b200_ctx* s) { return cafe_b200_set_error_model(s, probs, rows, max_cnt); });
+    if (rc == CAFE_B200_OK) g->have_em = probs != nullptr;
+    return rc;
+}
+
+int eval_base(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double* neg_lnl, double* family_lnl)
+{
+    if (!neg_lnl) { g->err = "null argument"; return CAFE_B200_ERR_ARG; }
+    std::vector<double> neg(g->shards.size(), 0.0);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+        return cafe_b200_eval_base(s, lambdas, n_lambda, &neg[i], family_lnl ? family_lnl + g->shard_begin[i] : nullptr);
+    });
+    if (rc == CAFE_B200_OK) *neg_lnl = combine(neg);
+    return rc;
+}
+
+int eval_gamma(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
+               int32_t n_cat, double* neg_lnl, double* cat_lk, double* family_lk, double* posterior, uint8_t* significant, uint8_t* failed,
+               int64_t* n_failed)
+{
+    if (!neg_lnl || n_cat < 1) { g->err = "null argument"; return CAFE_B200_ERR_ARG; }
+    const size_t n = g->shards.size();
+    std::vector<double> neg(n, 0.0);
+    std::vector<int64_t> nf(n, 0);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+        const size_t b = (size_t)g->shard_begin[i];
+        return cafe_b200_eval_gamma(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, &neg[i], cat_lk ? cat_lk + b * n_cat : nullptr,
+                                    family_lk ? family_lk + b : nullptr, posterior ? posterior + b * n_cat : nullptr,
+                                    significant ? significant + b * n_cat : nullptr, failed ? failed + b : nullptr, &nf[i]);
+    });
+    if (rc != CAFE_B200_OK) return rc;
+    *neg_lnl = combine(neg);      // a shard with a failed family reports +inf, and so does the sum (gamma_core.cpp:216-225)
+    if (n_failed) { *n_failed = 0; for (int64_t v : nf) *n_failed += v; }
+    return rc;
+}
+
+int enqueue_eval(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
+                 int32_t n_cat)
+{
+    return each(g, [&](int, cafe_b200_ctx* s) { return cafe_b200_enqueue_eval(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat); });
+}
+
+int fetch_result(cafe_b200_ctx* g, double* neg_lnl, int64_t* n_failed)
+{
+    const size_t n = g->shards.size();
+    std::vector<double> neg(n, 0.0);
+    std::vector<int64_t> nf(n, 0);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) { return cafe_b200_fetch_result(s, &neg[i], &nf[i]); });
+    if (rc != CAFE_B200_OK) return rc;
+    if (neg_lnl) *neg_lnl = combine(neg);
+    if (n_failed) { *n_failed = 0; for (int64_t v : nf) *n_failed += v; }
+    return rc;
+}
+
+int last_stats(cafe_b200_ctx* g, int32_t* n_launches, int32_t* n_matrices, float* ms_matrices, float* ms_prune)
+{
+    const size_t n = g->shards.size();
+    std::vector<int32_t> nl(n, 0), nm(n, 0);
+    std::vector<float> a(n, 0.f), b(n, 0.f);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) { return cafe_b200_last_stats(s, &nl[i], &nm[i], &a[i], &b[i]); });
+    if (rc != CAFE_B200_OK) return rc;
+    if (n_launches) { *n_launches = 0; for (int32_t v : nl) *n_launches += v; }       // kernels launched on all devices
+    if (n_matrices) *n_matrices = nm[0];                                               // per device (every device regenerates them)
+    if (ms_matrices) *ms_matrices = *std::max_element(a.begin(), a.end());             // slowest device
+    if (ms_prune) *ms_prune = *std::max_element(b.begin(), b.end());
+    return rc;
+}
+
+int root_vectors(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double multiplier, double* out)
+{
+    if (!out) { g->err = "bad argument"; return CAFE_B200_ERR_ARG; }
+    return each(g, [&](int i, cafe_b200_ctx* s) {
+        return cafe_b200_root_vectors(s, lambdas, n_lambda, multiplier, out + (size_t)g->shard_begin[i] * s->R);
+    });
+}
+
+int reconstruct(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs, int32_t n_cat,
+                int32_t* cat_states, int32_t* states, double* averaged)
+{
+    if (!states) { g->err = "bad argument"; return CAFE_B200_ERR_ARG; }
+    const size_t K = n_cat > 0 ? n_cat : 1, nn = (size_t)g->n_nodes;
+    return each(g, [&](int i, cafe_b200_ctx* s) {
+        const size_t b = (size_t)g->shard_begin[i];
+        return cafe_b200_reconstruct(s, lambdas, n_lambda, multipliers, cat_probs, n_cat, cat_states ? cat_states + b * K * nn : nullptr,
+                                     states + b * nn, averaged ? averaged + b * nn : nullptr);
+    });
+}
+
+}  // namespace group

@@ -9,10 +9,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -60,9 +64,81 @@ struct KeyPlan {
     std::vector<int32_t> mat_of;           // [K][n_nodes]
 };
 
+// One worker thread per device shard of a cafe_b200_create_multi context: a call on the group runs the single-device entry point
+// of every shard at the same time (each worker owns its device's stream; CUDA's current device is per thread).
+class ShardPool {
+public:
+    explicit ShardPool(int n) : rc_(n, 0)
+    {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~ShardPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // runs fn(i) on worker i for every shard and returns the first non-zero result (in shard order), 0 when all succeeded
+    int run(const std::function<int(int)>& fn, int* failed_shard = nullptr)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            pending_ = (int)workers_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+        for (size_t i = 0; i < rc_.size(); ++i)
+            if (rc_[i] != 0) { if (failed_shard) *failed_shard = (int)i; return rc_[i]; }
+        return 0;
+    }
+private:
+    void loop(int i)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<int(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            const int rc = (*fn)(i);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                rc_[i] = rc;
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::vector<int> rc_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<int(int)>* fn_ = nullptr;
+    unsigned long generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace cafe
 
 struct cafe_b200_ctx {
+    // cafe_b200_create_multi: a group context owns one single-device context per shard and nothing on any device itself
+    std::vector<cafe_b200_ctx*> shards;
+    std::vector<int64_t> shard_begin;      // [n_shards + 1] first family of every shard
+    cafe::ShardPool* pool = nullptr;
+    bool is_group() const { return !shards.empty(); }
+
     int device = 0;
     int n_sms = 0;
     cudaStream_t stream = nullptr;

@@ -2,6 +2,8 @@
 the root filter, the error-model table and root priors.  Behaviour follows the reference (cited per
 function); the numbers produced here are what crosses the C ABI.
 """
+import math
+
 import numpy as np
 
 
@@ -99,6 +101,28 @@ def rootdist_prior(rootdist):
     for s, c in rootdist.items():
         out[s] = np.float32(c) / np.float32(total)
     return out
+
+
+def poisson_prior(poisson_lambda, num_values):
+    """Poisson prior table (`-p<lambda>`; src/root_equilibrium_distribution.cpp:56-68, poisspdf src/poisson.cpp:21-24): entry i is
+    pdf(i) for every i the reference visits while it fills `num_values` simulated roots (each pdf(i) contributes
+    ceil(pdf(i) * num_values) of them), plus five more.  NB the reference weights root size j+1 with entry j in inference
+    (base_model.cpp:84, gamma_core.cpp:156) and root size j with entry j in Pupko (gene_family_reconstructor.cpp:65): the table is
+    uploaded as it is, the conventions live in the kernels.  float32 because compute() returns float."""
+    def pdf(x):
+        return math.exp(x * math.log(poisson_lambda) - math.lgamma(x + 1) - poisson_lambda)
+    table, filled, i = [], 0, 0
+    while filled < num_values:
+        pct = pdf(i)
+        j = 0
+        while j < pct * num_values:       # `for (size_t j = 0; j < pct * num_values; ++j)`
+            j += 1
+        filled += j
+        table.append(pct)
+        i += 1
+    for _ in range(5):
+        table.append(pdf(len(table)))
+    return np.asarray(table, dtype=np.float64).astype(np.float32)
 
 
 def read_error_model(path):

@@ -38,8 +38,9 @@ namespace cafe_b200_shim {
 // Owns one cafe_b200_ctx built from the reference's own objects.
 class device_context {
 public:
+    // devices: CUDA ordinals; more than one shards the families over them (cafe_b200_create_multi)
     device_context(const clade* p_tree, const lambda* p_lambda, const std::vector<gene_family>& families,
-                   int max_family_size, int max_root_family_size, int device)
+                   int max_family_size, int max_root_family_size, const std::vector<int>& devices)
         : _max_family_size(max_family_size), _max_root_family_size(max_root_family_size)
     {
         _order.assign(p_tree->reverse_level_begin(), p_tree->reverse_level_end());
@@ -70,9 +71,11 @@ public:
         for (size_t f = 0; f < _n_families; ++f)
             for (size_t j = 0; j < species.size(); ++j) counts[f * species.size() + j] = families[f].get_species_size(species[j]);
         cafe_b200_tree t{n, parent.data(), branch_length.data(), leaf_col.data(), lambda_class.data()};
-        if (cafe_b200_create(&t, counts.data(), int64_t(_n_families), int32_t(species.size()), max_family_size, max_root_family_size,
-                             device, &_ctx) != CAFE_B200_OK)
-            throw std::runtime_error(std::string("cafe_b200_create: ") + cafe_b200_last_error(nullptr));
+        std::vector<int32_t> devs(devices.begin(), devices.end());
+        if (devs.empty()) devs.push_back(0);
+        if (cafe_b200_create_multi(&t, counts.data(), int64_t(_n_families), int32_t(species.size()), max_family_size, max_root_family_size,
+                                   devs.data(), int32_t(devs.size()), &_ctx) != CAFE_B200_OK)
+            throw std::runtime_error(std::string("cafe_b200_create_multi: ") + cafe_b200_last_error(nullptr));
     }
     ~device_context() { cafe_b200_destroy(_ctx); }
     device_context(const device_context&) = delete;
@@ -117,18 +120,18 @@ private:
 
 class gpu_base_model : public base_model {
     std::unique_ptr<device_context> _dev;
-    int _device;
+    std::vector<int> _devices;
 
     device_context& dev(const lambda* p_lambda)
     {
-        if (!_dev) _dev.reset(new device_context(_p_tree, p_lambda, *_p_gene_families, _max_family_size, _max_root_family_size, _device));
+        if (!_dev) _dev.reset(new device_context(_p_tree, p_lambda, *_p_gene_families, _max_family_size, _max_root_family_size, _devices));
         return *_dev;
     }
 
 public:
     gpu_base_model(lambda* p_lambda, const clade* p_tree, const std::vector<gene_family>* p_gene_families, int max_family_size,
-                   int max_root_family_size, error_model* p_error_model, int device = 0)
-        : base_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, p_error_model), _device(device)
+                   int max_root_family_size, error_model* p_error_model, const std::vector<int>& devices = std::vector<int>(1, 0))
+        : base_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, p_error_model), _devices(devices)
     {
     }
 
@@ -154,7 +157,7 @@ public:
 
     reconstruction* reconstruct_ancestral_states(const user_data& ud, const input_parameters& ui, matrix_cache*) override
     {
-        device_context d(_p_tree, _p_lambda, ud.gene_families, _max_family_size, _max_root_family_size, _device);
+        device_context d(_p_tree, _p_lambda, ud.gene_families, _max_family_size, _max_root_family_size, _devices);
         d.sync_inputs(ud.prior, nullptr);
         std::vector<double> lambdas = get_lambda_values(_p_lambda);
         const size_t n = d.order().size();
@@ -172,19 +175,20 @@ public:
 
 class gpu_gamma_model : public gamma_model {
     std::unique_ptr<device_context> _dev;
-    int _device;
+    std::vector<int> _devices;
 
     device_context& dev(const lambda* p_lambda)
     {
-        if (!_dev) _dev.reset(new device_context(_p_tree, p_lambda, *_p_gene_families, _max_family_size, _max_root_family_size, _device));
+        if (!_dev) _dev.reset(new device_context(_p_tree, p_lambda, *_p_gene_families, _max_family_size, _max_root_family_size, _devices));
         return *_dev;
     }
 
 public:
     gpu_gamma_model(lambda* p_lambda, clade* p_tree, std::vector<gene_family>* p_gene_families, int max_family_size,
-                    int max_root_family_size, int n_gamma_cats, double fixed_alpha, error_model* p_error_model, int device = 0)
+                    int max_root_family_size, int n_gamma_cats, double fixed_alpha, error_model* p_error_model,
+                    const std::vector<int>& devices = std::vector<int>(1, 0))
         : gamma_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, n_gamma_cats, fixed_alpha, p_error_model),
-          _device(device)
+          _devices(devices)
     {
     }
 
@@ -226,7 +230,7 @@ public:
 
     reconstruction* reconstruct_ancestral_states(const user_data& ud, const input_parameters& ui, matrix_cache*) override
     {
-        device_context d(_p_tree, _p_lambda, ud.gene_families, _max_family_size, _max_root_family_size, _device);
+        device_context d(_p_tree, _p_lambda, ud.gene_families, _max_family_size, _max_root_family_size, _devices);
         d.sync_inputs(ud.prior, nullptr);
         std::vector<double> lambdas = get_lambda_values(_p_lambda);
         const std::vector<double> multipliers = get_lambda_multipliers();

@@ -305,6 +305,48 @@ inline std::map<int, int> read_rootdist(std::istream& in)
     return out;
 }
 
+// ---- root priors (root_equilibrium_distribution, src/root_equilibrium_distribution.cpp:13-87; chosen by user_data::create_prior,
+// src/user_data.cpp:176-206).  A table holds compute(j) for j = 0 .. size-1 as the FLOAT compute() returns (.h:40); beyond it the
+// prior is 0.  The index conventions stay in the kernels: inference weights root size j+1 with entry j (base_model.cpp:84,
+// gamma_core.cpp:156), Pupko's root weights size j with entry j (gene_family_reconstructor.cpp:65). ----
+// default: uniform over sizes 0 .. max_root_family_size-1, each float(1)/float(n) (:30-35, 71-79)
+inline std::vector<float> uniform_prior(int max_root_family_size)
+{
+    return std::vector<float>((size_t)max_root_family_size, float(1) / float(max_root_family_size));
+}
+
+// `-f`: a {size: count} root distribution; entry i = float(count_i) / float(total) (:13-28, 71-79)
+inline std::vector<float> rootdist_prior(const std::map<int, int>& rootdist)
+{
+    if (rootdist.empty()) throw std::runtime_error("No root distribution specified");
+    size_t total = 0;
+    for (const auto& kv : rootdist) total += (size_t)std::max(kv.second, 0);
+    std::vector<float> out((size_t)rootdist.rbegin()->first + 1, 0.0f);
+    for (const auto& kv : rootdist)
+        if (kv.first >= 0 && kv.second > 0) out[(size_t)kv.first] = float((size_t)kv.second) / float(total);
+    return out;
+}
+
+// `-p<lambda>`: entry i = poisspdf(i, lambda) = exp(i log(lambda) - lgamma(i + 1) - lambda) (src/poisson.cpp:21-24) for every i the
+// reference visits while it fills num_values simulated roots (pdf(i) contributes the smallest integer count >= pdf(i) * num_values),
+// and five more (:56-68)
+inline std::vector<float> poisson_prior(double poisson_lambda, size_t num_values)
+{
+    auto pdf = [poisson_lambda](size_t x) { return std::exp(double(x) * std::log(poisson_lambda) - std::lgamma(double(x) + 1) - poisson_lambda); };
+    std::vector<float> out;
+    size_t filled = 0;
+    for (size_t i = 0; filled < num_values; ++i) {
+        const double pct = pdf(i);
+        size_t j = 0;
+        while (double(j) < pct * double(num_values)) ++j;
+        filled += j;
+        out.push_back(float(pct));
+        if (i > 100000) throw std::runtime_error("Poisson prior does not fill the requested number of values");
+    }
+    for (int i = 0; i < 5; ++i) out.push_back(float(pdf(out.size())));
+    return out;
+}
+
 // ---- result tables -----------------------------------------------------------------------------------------------------------------
 // lambda::to_string (src/lambda.cpp:25-30, 47-58): setw(15) << setprecision(14) applied to the first value only by setw
 inline std::string lambdas_to_string(const std::vector<double>& lambdas)

@@ -90,6 +90,33 @@ int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
+int cafe_b200_io_make_prior(int32_t kind, double poisson_lambda, const char* rootdist_path, int32_t num_values, float* prior, int32_t cap,
+                            int32_t* n)
+{
+    try {
+        if (!n) throw std::runtime_error("null argument");
+        std::vector<float> t;
+        if (kind == 0) {
+            if (num_values < 1) throw std::runtime_error("uniform prior needs a positive number of root sizes");
+            t = cafe_b200_host::uniform_prior(num_values);
+        } else if (kind == 1) {
+            if (!rootdist_path) throw std::runtime_error("null path");
+            std::ifstream in(rootdist_path);
+            if (!in) throw std::runtime_error(std::string("Failed to open ") + rootdist_path);
+            t = cafe_b200_host::rootdist_prior(cafe_b200_host::read_rootdist(in));
+        } else if (kind == 2) {
+            if (!(poisson_lambda > 0) || num_values < 1) throw std::runtime_error("Poisson prior needs lambda > 0 and a positive number of values");
+            t = cafe_b200_host::poisson_prior(poisson_lambda, (size_t)num_values);
+        } else throw std::runtime_error("unknown prior kind");
+        *n = (int32_t)t.size();
+        if (prior) {
+            if ((int32_t)t.size() > cap) { g_io_error = "output buffer too small"; return CAFE_B200_ERR_RANGE; }
+            std::memcpy(prior, t.data(), t.size() * sizeof(float));
+        }
+        return CAFE_B200_OK;
+    } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
+}
+
 int cafe_b200_io_derive_sizes(const int32_t* counts, int64_t n, int32_t* max_family_size, int32_t* max_root_family_size)
 {
     if (!counts || !max_family_size || !max_root_family_size) return CAFE_B200_ERR_ARG;

@@ -52,6 +52,19 @@ def read_error_model(path, rows_cap=100000):
     return probs[:rows.value].copy(), mx.value
 
 
+def make_prior(kind, num_values=0, poisson_lambda=0.0, rootdist_path=None):
+    """float32 prior table built by the library as the reference builds it: kind 'uniform' | 'rootdist' | 'poisson'."""
+    L = _lib.load()
+    k = {"uniform": 0, "rootdist": 1, "poisson": 2}[kind]
+    n = C.c_int32()
+    path = None if rootdist_path is None else str(rootdist_path).encode()
+    L.cafe_b200_io_make_prior.argtypes = [C.c_int32, C.c_double, C.c_char_p, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]
+    _check(L, L.cafe_b200_io_make_prior(k, float(poisson_lambda), path, int(num_values), None, 0, C.byref(n)))
+    out = np.zeros(n.value, dtype=np.float32)
+    _check(L, L.cafe_b200_io_make_prior(k, float(poisson_lambda), path, int(num_values), out.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n)))
+    return out
+
+
 def derive_sizes(counts):
     L = _lib.load()
     c = np.ascontiguousarray(counts, dtype=np.int32)

@@ -88,9 +88,10 @@ class error_model:
 
 
 class Context:
-    """Owns one cafe_b200_ctx (one GPU, one shard of families)."""
+    """Owns one cafe_b200_ctx: one GPU (device=...), or the families sharded over several GPUs of the node from this one process
+    (devices=[...], cafe_b200_create_multi)."""
 
-    def __init__(self, tree, counts, max_family_size, max_root_family_size, device=0):
+    def __init__(self, tree, counts, max_family_size, max_root_family_size, device=0, devices=None):
         self.lib = _lib.load()
         self._pinned_bufs = {}
         self.tree = tree
@@ -103,8 +104,13 @@ class Context:
                       np.ascontiguousarray(tree.leaf_col, dtype=np.int32), np.ascontiguousarray(tree.lambda_class, dtype=np.int32))
         ct = _lib.CTree(tree.n_nodes, _lib.ip(self._keep[0]), _lib.dp(self._keep[1]), _lib.ip(self._keep[2]), _lib.ip(self._keep[3]))
         h = C.c_void_p()
-        rc = self.lib.cafe_b200_create(C.byref(ct), _lib.ip(counts), self.F, self.n_species, self.max_family_size, self.R,
-                                       int(device), C.byref(h))
+        if devices is None:
+            rc = self.lib.cafe_b200_create(C.byref(ct), _lib.ip(counts), self.F, self.n_species, self.max_family_size, self.R,
+                                           int(device), C.byref(h))
+        else:
+            devs = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self.lib.cafe_b200_create_multi(C.byref(ct), _lib.ip(counts), self.F, self.n_species, self.max_family_size, self.R,
+                                                 _lib.ip(devs), len(devs), C.byref(h))
         if rc:
             raise CafeError("cafe_b200_create: %s (status %d)" % (self.lib.cafe_b200_last_error(None).decode(), rc))
         self.h = h
@@ -141,6 +147,9 @@ class Context:
 
     def unique_families(self):
         return self.lib.cafe_b200_unique_families(self.h)
+
+    def n_devices(self):
+        return self.lib.cafe_b200_n_devices(self.h)
 
     def eval_base(self, lambdas, want_family=True):
         lam = _lib.as_f64(lambdas)

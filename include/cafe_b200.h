@@ -20,7 +20,8 @@
  *     neg_lnl = +inf exactly as the reference returns -log(0) (base_model.cpp:56-60,
  *     gamma_core.cpp:174-178,216-225).
  *   - caller owns every output buffer; NULL means "not wanted".
- *   - one context per host thread / per GPU; a context is bound to one CUDA device.
+ *   - one context per host thread; a context is bound to one CUDA device (cafe_b200_create) or shards its families over
+ *     several devices of the node (cafe_b200_create_multi).
  *   - there is no CPU fallback: create fails with CAFE_B200_ERR_CUDA when no device is usable.
  *
  * Tree layout: nodes in the reference's reverse level order (src/clade.cpp:69-100): children
@@ -63,6 +64,21 @@ typedef struct {
  * src/user_data.cpp:40-48.  device: CUDA ordinal. */
 int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
                      int32_t max_family_size, int32_t max_root_family_size, int32_t device, cafe_b200_ctx** out);
+
+/* The same model spread over several GPUs of one node from ONE host thread (the reference's only parallel axis is the
+ * family loop, `#pragma omp parallel for` at src/base_model.cpp:69 and src/gamma_core.cpp:190): families are split into n_devices
+ * contiguous shards, shard i lives on devices[i] with its own stream, every device regenerates the (small) matrices itself, and each
+ * call below launches on all devices before it waits for any.  The only cross-device step is the final sum of base_model.cpp:95 /
+ * gamma_core.cpp:233: the per-device partial sums {sum lnL, n_failed} (16 bytes each) are added on the host in device order, so a
+ * score is bit-reproducible for a given device list.  Per-family outputs are written straight into the caller's buffers at the
+ * shard's offset.  The returned handle is used with every other entry point of this header exactly like a single-device context
+ * (simulate, get_matrix and the stream / stats hooks act on the first device).  n_devices == 1 is cafe_b200_create. */
+int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                           int32_t max_family_size, int32_t max_root_family_size, const int32_t* devices, int32_t n_devices,
+                           cafe_b200_ctx** out);
+
+/* Number of device shards behind a context (1 for cafe_b200_create). */
+int32_t cafe_b200_n_devices(const cafe_b200_ctx* ctx);
 
 int cafe_b200_destroy(cafe_b200_ctx* ctx);
 
@@ -182,6 +198,14 @@ int cafe_b200_io_read_families(const char* path, int64_t* n_families, int32_t* n
 
 /* Error-model file (src/io.cpp:228-274, src/error_model.cpp:31-50): probs[rows x 3]. */
 int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_cap, int32_t* rows, int32_t* max_count);
+
+/* The root prior table cafe_b200_set_prior takes, built as the reference builds it (user_data::create_prior, src/user_data.cpp:176-206;
+ * root_equilibrium_distribution, src/root_equilibrium_distribution.cpp:13-87).  kind 0: uniform over num_values root sizes (the default,
+ * num_values = max_root_family_size); 1: `-f` root distribution file ("size count" lines, src/user_data.cpp:105-117);
+ * 2: `-p<lambda>` Poisson(poisson_lambda) with num_values = max_root_family_size.  prior[cap] receives the table (NULL: only its
+ * length n); entries beyond n are 0 for the model. */
+int cafe_b200_io_make_prior(int32_t kind, double poisson_lambda, const char* rootdist_path, int32_t num_values, float* prior, int32_t cap,
+                            int32_t* n);
 
 /* max_family_size / max_root_family_size from the count table (src/user_data.cpp:40-48, floors src/user_data.h:26-27). */
 int cafe_b200_io_derive_sizes(const int32_t* counts, int64_t n, int32_t* max_family_size, int32_t* max_root_family_size);

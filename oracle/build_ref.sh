@@ -40,23 +40,28 @@ FLAGS=(-std=c++11 -O2 -fopenmp -fPIC -w -fno-access-control -include "$OUT/confi
        -DOPTIMIZER_STRATEGY=NelderMead -DDISCRETIZATION_RANGE=200 -DMAX_STACK_FAMILY_SIZE=1000)
 objs=()
 pids=()
+SHIM_OBJ="$OUT/obj/ref_gpu_model.o"
 for src in "$REF"/src/*.cpp "$HERE/ref_driver.cpp" "$HERE/ref_gpu_model.cpp"; do
   [ -f "$src" ] || continue
   obj="$OUT/obj/$(basename "${src%.cpp}").o"
-  objs+=("$obj")
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../cafe5_b200/host/gpu_model.hpp" -nt "$obj" ]; then
-    "$CXX" "${FLAGS[@]}" -c "$src" -o "$obj" &
+  [ "$obj" = "$SHIM_OBJ" ] || objs+=("$obj")
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../cafe5_b200/host/gpu_model.hpp" -nt "$obj" ] || [ "$HERE/../include/cafe_b200.h" -nt "$obj" ] \
+     || [ "$HERE/ref_optimize.hpp" -nt "$obj" ] || [ "$HERE/ref_ctx.hpp" -nt "$obj" ]; then
+    "$CXX" "${FLAGS[@]}" -I"$HERE" -c "$src" -o "$obj" &
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-# the drop-in shim (ref_gpu_model.cpp) binds the product's C ABI: link libcafe_b200.so when it has been built
-LINK_GPU=()
-if [ -f "$HERE/../cafe5_b200/libcafe_b200.so" ]; then
-  LINK_GPU=(-L"$HERE/../cafe5_b200" -lcafe_b200 '-Wl,-rpath,$ORIGIN/../../cafe5_b200')
-else
-  echo "libcafe_b200.so not built yet: build it first (python -c 'import __graft_entry__ as g; g.build()')" >&2
-  exit 1
-fi
-"$CXX" -shared -fopenmp -o "$OUT/libcafe_ref.so" "${objs[@]}" "${LINK_GPU[@]}" -lz -ldl
+fail=0
+for p in "${pids[@]:-}"; do [ -n "$p" ] && { wait "$p" || fail=1; }; done
+[ "$fail" = 0 ] || { echo "compilation failed" >&2; exit 1; }
+# 1. the unmodified reference + its driver: no product code inside, nothing of the product linked
+"$CXX" -shared -fopenmp -o "$OUT/libcafe_ref.so" "${objs[@]}" -lz -ldl
 echo "built $OUT/libcafe_ref.so"
+# 2. the drop-in shim's test driver binds the product's C ABI: its own library, on top of (1) and libcafe_b200.so
+if [ -f "$HERE/../cafe5_b200/libcafe_b200.so" ]; then
+  "$CXX" -shared -fopenmp -o "$OUT/libcafe_ref_shim.so" "$SHIM_OBJ" -L"$OUT" -lcafe_ref -L"$HERE/../cafe5_b200" -lcafe_b200 \
+      '-Wl,-rpath,$ORIGIN' '-Wl,-rpath,$ORIGIN/../../cafe5_b200'
+  echo "built $OUT/libcafe_ref_shim.so"
+else
+  echo "libcafe_b200.so not built yet: libcafe_ref_shim.so skipped (python -c 'import __graft_entry__ as g; g.build()')" >&2
+fi

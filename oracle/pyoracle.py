@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libcafe_ref.so")
+REF_SHIM_SO = os.path.join(HERE, "_ref", "libcafe_ref_shim.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -247,7 +248,9 @@ class RefLib:
         L.ref_reconstruct_gamma.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, c_dp, C.c_int, c_ip, c_ip, c_dp]
         L.ref_set_threads.argtypes = [C.c_int]
         L.ref_max_threads.restype = C.c_int
-        L.ref_optimize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, c_dp, c_ip, c_dp, c_ip, c_ip, c_dp]
+        L.ref_optimize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, c_dp, c_ip, c_dp, c_ip, c_ip, c_dp,
+                                   c_dp, c_dp, c_ip, c_ip, C.c_int, c_ip]
+        self._shim = None
         L.ref_ctx_error.restype = C.c_char_p
         L.ref_ctx_error.argtypes = [C.c_void_p]
         L.ref_time_precalculate.restype = C.c_double
@@ -261,6 +264,19 @@ class RefLib:
     def _check(self, rc):
         if rc:
             raise RuntimeError("reference: " + self.lib.ref_last_error().decode())
+
+    def shim(self):
+        """oracle/_ref/libcafe_ref_shim.so: the product's drop-in models (cafe5_b200/host/gpu_model.hpp) compiled against the
+        unmodified reference.  A separate library, loaded only when a test asks for the 'gpu' backend, so that libcafe_ref.so
+        (the CPU baseline) never maps libcafe_b200.so."""
+        if self._shim is None:
+            if not os.path.exists(REF_SHIM_SO):
+                raise RuntimeError("oracle/_ref/libcafe_ref_shim.so missing (run oracle/build_ref.sh after building libcafe_b200.so)")
+            C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)
+            self._shim = C.CDLL(REF_SHIM_SO)
+            self._shim.ref_optimize_gpu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, c_ip, C.c_int, c_dp, c_ip, c_dp, c_ip, c_ip,
+                                                    c_dp, c_dp, c_dp, c_ip, c_ip, C.c_int, c_ip]
+        return self._shim
 
     def birthdeath(self, s, c, log_alpha, coeff):
         return self.lib.ref_birthdeath_rate_with_log_alpha(s, c, log_alpha, coeff)
@@ -281,6 +297,18 @@ class RefLib:
         m = np.empty(K)
         self.lib.ref_get_gamma(K, alpha, _dp(p), _dp(m))
         return p, m
+
+    def prior_table(self, kind, num_values=0, poisson_lambda=0.0, rootdist=None, cap=512):
+        """compute(j), j < cap, of the prior the reference builds: kind 'uniform' (num_values sizes), 'rootdist' ({size: count}),
+        'poisson' (poisson_lambda, num_values).  Returns (float32 table trimmed to the sizes it covers, full cap-long array)."""
+        out = np.zeros(cap, dtype=np.float32)
+        tl = C.c_int()
+        sizes = np.ascontiguousarray(sorted(rootdist) if rootdist else [0], dtype=np.int32)
+        cnts = np.ascontiguousarray([rootdist[int(k)] for k in sizes] if rootdist else [0], dtype=np.int32)
+        self.lib.ref_prior_table.argtypes = [C.c_int, C.c_double, c_ip, c_ip, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, c_ip]
+        self._check(self.lib.ref_prior_table({"uniform": 0, "rootdist": 1, "poisson": 2}[kind], float(poisson_lambda), _ip(sizes), _ip(cnts),
+                                             len(sizes) if rootdist else 0, int(num_values), _fp(out), cap, C.byref(tl)))
+        return out[:tl.value].copy(), out
 
     def set_threads(self, n):
         self.lib.ref_set_threads(n)
@@ -392,16 +420,36 @@ class RefLib:
                                                         C.byref(neg), _dp(cat), _up(failed)))
             return dict(neg_lnl=neg.value, cat_lk=cat, failed=failed)
 
-        def optimize(self, backend, n_cat=0, optimize_epsilon=False, seed=10, device=0):
-            """Run the reference's optimizer (Nelder-Mead) with backend 'cpu' (reference models) or 'gpu' (CUDA shim)."""
+        def optimize(self, backend, n_cat=0, optimize_epsilon=False, seed=10, device=0, devices=None, trace=False, trace_cap=4096):
+            """Run the reference's optimizer (Nelder-Mead) with backend 'cpu' (the reference's models) or 'gpu' (the CUDA drop-in
+            models on `devices`, default [device]).  trace=True also returns every attempt: values[n, n_values], scores[n],
+            failed_family[n] (lowest index of a family whose likelihood was 0; -1 none), n_failed[n]."""
             vals = np.zeros(16)
-            nv, iters, attempts = C.c_int(), C.c_int(), C.c_int()
+            nv, iters, attempts, tn = C.c_int(), C.c_int(), C.c_int(), C.c_int()
             score, secs = C.c_double(), C.c_double()
-            rc = self.ref.lib.ref_optimize(self.h, 1 if backend == "gpu" else 0, int(n_cat), 1 if optimize_epsilon else 0, int(seed),
-                                           int(device), _dp(vals), C.byref(nv), C.byref(score), C.byref(iters), C.byref(attempts), C.byref(secs))
+            cap = int(trace_cap) if trace else 0
+            tv = np.zeros((max(cap, 1), 16))
+            ts = np.zeros(max(cap, 1))
+            tf = np.zeros(max(cap, 1), dtype=np.int32)
+            tc = np.zeros(max(cap, 1), dtype=np.int32)
+            targs = (_dp(tv), _dp(ts), _ip(tf), _ip(tc), cap, C.byref(tn)) if trace else (None, None, None, None, 0, C.byref(tn))
+            if backend == "gpu":
+                devs = np.ascontiguousarray(devices if devices is not None else [device], dtype=np.int32)
+                rc = self.ref.shim().ref_optimize_gpu(self.h, int(n_cat), 1 if optimize_epsilon else 0, int(seed), _ip(devs), len(devs),
+                                                      _dp(vals), C.byref(nv), C.byref(score), C.byref(iters), C.byref(attempts),
+                                                      C.byref(secs), *targs)
+            else:
+                rc = self.ref.lib.ref_optimize(self.h, int(n_cat), 1 if optimize_epsilon else 0, int(seed), _dp(vals), C.byref(nv),
+                                               C.byref(score), C.byref(iters), C.byref(attempts), C.byref(secs), *targs)
             if rc:
                 raise RuntimeError("ref_optimize: " + self.ref.lib.ref_ctx_error(self.h).decode())
-            return dict(values=vals[:nv.value].copy(), score=score.value, iterations=iters.value, attempts=attempts.value, seconds=secs.value)
+            out = dict(values=vals[:nv.value].copy(), score=score.value, iterations=iters.value, attempts=attempts.value, seconds=secs.value)
+            if trace:
+                n = tn.value
+                # the tracing scorer stores rows of n_values doubles back to back
+                flat = tv.reshape(-1)[:n * nv.value].reshape(n, nv.value).copy()
+                out["trace"] = dict(values=flat, scores=ts[:n].copy(), failed_family=tf[:n].copy(), n_failed=tc[:n].copy())
+            return out
 
         def write_outputs(self, lambdas, multipliers=None, cat_probs=None, alpha=0.0):
             """(family_likelihoods text, results text, category_likelihoods text) exactly as the reference writes them."""

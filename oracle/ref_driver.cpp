@@ -50,6 +50,8 @@
 #include "newick_ape_loader.h"
 #include "optimizer_scorer.h"
 
+#include "ref_optimize.hpp"
+
 INITIALIZE_EASYLOGGINGPP
 
 std::mt19937 randomizer_engine(10);  // the reference's main.cpp seeds from random_device; we seed explicitly
@@ -81,16 +83,6 @@ std::vector<std::string> split(const std::string& s, char d)
     return out;
 }
 
-struct ref_ctx {
-    std::unique_ptr<clade> tree;
-    std::unique_ptr<clade> lambda_tree;
-    std::vector<const clade*> order;          // reverse level order
-    int max_family_size = 0, max_root_family_size = 0;
-    std::unique_ptr<error_model> em;
-    user_data ud;
-    input_parameters ui;
-    std::string err;
-};
 
 lambda* make_lambda(ref_ctx* c, const double* lambdas, int n)
 {
@@ -187,6 +179,28 @@ int ref_tree_flatten(const char* newick, const char* lambda_newick, int* parent,
         }
         if (int(names.size()) + 1 > names_cap) { g_err = "names buffer too small"; return 2; }
         std::strcpy(names_out, names.c_str());
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// The prior tables the reference builds (src/root_equilibrium_distribution.cpp:13-68, selected by user_data::create_prior,
+// src/user_data.cpp:176-206): kind 0 = uniform over num_values sizes, 1 = user root distribution {sizes[i]: counts[i]} (`-f`),
+// 2 = Poisson(poisson_lambda) over num_values simulated roots (`-p<lambda>`).  out[j] = compute(j) for j < cap (a float, .h:40);
+// table_len = number of sizes the table covers (compute returns 0 beyond it, .cpp:81-87).
+int ref_prior_table(int kind, double poisson_lambda, const int* sizes, const int* counts, int n, int num_values, float* out, int cap,
+                    int* table_len)
+{
+    ensure_init();
+    try {
+        std::unique_ptr<root_equilibrium_distribution> p;
+        if (kind == 0) p.reset(new root_equilibrium_distribution((size_t)num_values));
+        else if (kind == 1) {
+            std::map<int, int> m;
+            for (int i = 0; i < n; ++i) m[sizes[i]] = counts[i];
+            p.reset(new root_equilibrium_distribution(m));
+        } else p.reset(new root_equilibrium_distribution(poisson_lambda, (size_t)num_values));
+        for (int j = 0; j < cap; ++j) out[j] = p->compute(j);
+        if (table_len) *table_len = (int)p->_frequency_percentage.size();
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }
@@ -670,7 +684,59 @@ double ref_session_prune(void* h, void* sh, long n, double* sum_lnl)
     } catch (std::exception& e) { g_err = e.what(); return -1.0; }
 }
 
+// The reference's optimizer over the reference's own CPU models (the CUDA counterpart lives in libcafe_ref_shim.so, ref_gpu_model.cpp).
+// trace_* (optional, trace_cap rows): every attempt the optimizer made, in order.
+int ref_optimize(void* h, int n_cat, int optimize_epsilon, unsigned seed, double* values_out, int* n_values, double* score,
+                 int* iterations, int* attempts, double* seconds, double* trace_values, double* trace_scores, int* trace_failed_family,
+                 int* trace_n_failed, int trace_cap, int* trace_n)
+{
+    auto c = (ref_ctx*)h;
+    ref_opt::trace_buffer tb;
+    tb.values = trace_values; tb.scores = trace_scores; tb.failed_family = trace_failed_family; tb.n_failed = trace_n_failed;
+    tb.cap = trace_values ? trace_cap : 0;
+    auto make = [&](user_data& ud, int k, error_model* p_em) -> model* {
+        if (k > 1) return new gamma_model(nullptr, c->tree.get(), &ud.gene_families, ud.max_family_size, ud.max_root_family_size, k, -1.0, p_em);
+        return new base_model(nullptr, c->tree.get(), &ud.gene_families, ud.max_family_size, ud.max_root_family_size, p_em);
+    };
+    const int rc = ref_opt::run(c, make, n_cat, optimize_epsilon, seed, values_out, n_values, score, iterations, attempts, seconds, &tb);
+    if (trace_n) *trace_n = tb.n;
+    return rc;
+}
+
+const char* ref_ctx_error(void* h) { return ((ref_ctx*)h)->err.c_str(); }
+
 // Viterbi branch p-value (src/gene_family_reconstructor.cpp:390-429) restated through the matrix only:
 // kept out; "next" row f2.
 
 }  // extern "C"
+
+// ---- the reference's fminsearch over an arbitrary C callback: pins the product's simplex search (cafe5_b200/host/nelder_mead.hpp) ----
+namespace {
+class callback_scorer : public optimizer_scorer {
+    double (*_cb)(const double*, void*);
+    void* _user;
+    std::vector<double> _x0;
+public:
+    callback_scorer(double (*cb)(const double*, void*), void* user, const double* x0, int n) : _cb(cb), _user(user), _x0(x0, x0 + n) {}
+    std::vector<double> initial_guesses() override { return _x0; }
+    double calculate_score(const double* values) override { return _cb(values, _user); }
+};
+}
+
+extern "C" int ref_fminsearch(double (*cb)(const double*, void*), void* user, int n, const double* x0, int max_iterations,
+                              double* x_out, double* f_out, int* iterations)
+{
+    try {
+        callback_scorer scorer(cb, user, x0, n);
+        FMinSearch* pfm = fminsearch_new_with_eq(&scorer, n);
+        pfm->maxiters = max_iterations > 0 ? max_iterations : 300;   // optimizer_parameters::neldermead_iterations
+        std::vector<double> start(x0, x0 + n);
+        fminsearch_min(pfm, start.data());
+        candidate* best = get_best_result(pfm);
+        for (int i = 0; i < n; ++i) x_out[i] = best->values[i];
+        *f_out = best->score;
+        *iterations = pfm->iters;
+        fminsearch_free(pfm);
+        return 0;
+    } catch (std::exception&) { return 1; }
+}

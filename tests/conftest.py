@@ -33,7 +33,22 @@ def ref():
 
 @pytest.fixture(scope="session")
 def golden():
-    return {n: np.load(os.path.join(GOLDEN, n + ".npz")) for n in ("mammals", "hymenoptera", "matrices", "small")}
+    return {n: np.load(os.path.join(GOLDEN, n + ".npz")) for n in ("mammals", "hymenoptera", "matrices", "small", "priors")}
+
+
+def random_prior(rng, max_root_family_size):
+    """One of the three priors the reference can be run with (src/user_data.cpp:176-206), as the float32 table cafe_b200_set_prior
+    takes: uniform, a user root distribution with holes and a table shorter than max_root_family_size, or a Poisson prior."""
+    from cafe5_b200 import families as fam
+    kind = int(rng.integers(0, 3))
+    if kind == 0:
+        return fam.uniform_prior(max_root_family_size)
+    if kind == 1:
+        top = int(rng.integers(max(3, max_root_family_size // 3), max_root_family_size))
+        rd = {s: int(rng.choice([1, 2, 30, 700, 20000])) for s in range(1, top + 1) if rng.random() > 0.2}
+        rd[top] = 5
+        return fam.rootdist_prior(rd)
+    return fam.poisson_prior(float(rng.uniform(0.5, max_root_family_size / 3.0)), max_root_family_size)
 
 
 def ulp_distance(a, b):

@@ -34,7 +34,93 @@ def load_dataset(fam_path, tree_path, lambda_tree_path=None):
     return newick, lnewick, species, counts, mfs, mrs, int(keep.size)
 
 
+def spiky_rootdist(max_size, seed):
+    """A root distribution whose neighbouring sizes differ by orders of magnitude, with holes: an off-by-one in the prior index
+    (inference weights root size j+1 with compute(j), Pupko's root weights size j with compute(j)) changes every result."""
+    rng = np.random.default_rng(seed)
+    rd = {}
+    for s in range(1, max_size + 1):
+        if rng.random() < 0.15:
+            continue                                   # a hole: prior 0 inside the table
+        rd[s] = int(rng.choice([1, 3, 40, 1000, 25000]))
+    rd[max_size] = 7
+    return rd
+
+
+def make_priors():
+    """tests/golden/priors.npz: the reference's likelihoods and Pupko reconstructions under NON-UNIFORM priors -- a user root
+    distribution (`-f`) whose table is shorter than max_root_family_size (so compute() returns 0 beyond it) and Poisson priors
+    (`-p<lambda>`), tables built by the reference's own constructors (ref_prior_table)."""
+    build_ref()
+    ref = RefLib()
+    out = {}
+    small = np.load(os.path.join(OUT, "small.npz"))
+    mfs, mrs, lam = int(small["max_family_size"]), int(small["max_root_family_size"]), float(small["lambda"])
+    p3, m3 = ref.get_gamma(3, float(small["gamma_alpha"]))
+    rd_small = spiky_rootdist(30, 1)
+    priors = {"rootdist": ref.prior_table("rootdist", rootdist=rd_small)[0],
+              "poisson": ref.prior_table("poisson", mrs, 6.5)[0]}
+    out["small_rootdist_sizes"] = np.array(sorted(rd_small))
+    out["small_rootdist_counts"] = np.array([rd_small[k] for k in sorted(rd_small)])
+    out["small_poisson_lambda"] = 6.5
+    for pname, prior in priors.items():
+        assert len(prior) < mrs                                  # "0 beyond the table" must fire
+        out["small_%s_prior" % pname] = prior
+        for ti in range(4):
+            nw = str(small["t%d_newick" % ti])
+            tree = FlatTree(nw)
+            counts = small["t%d_counts" % ti]
+            c = ref.ctx(nw, tree.species, counts, mfs, mrs, prior.astype(np.float64))
+            b = c.eval_base([lam])
+            g = c.eval_gamma([lam], m3, p3)
+            rg = c.reconstruct_gamma([lam], m3, p3)
+            k = "small_%s_t%d_" % (pname, ti)
+            out[k + "ref_base"] = b["neg_lnl"]
+            out[k + "ref_family_lnl"] = b["family_lnl"]
+            out[k + "ref_gamma"] = g["neg_lnl"]
+            out[k + "ref_cat_lk"] = g["cat_lk"]
+            out[k + "ref_failed"] = g["failed"]
+            out[k + "ref_rec"] = c.reconstruct_base([lam])
+            out[k + "ref_rec_gamma"] = rg["states"]
+            out[k + "ref_rec_gamma_cat"] = rg["cat_states"]
+            c.close()
+    m = np.load(os.path.join(OUT, "mammals.npz"))
+    species = [str(x) for x in m["species"]]
+    counts = m["counts"].astype(np.int32)
+    sub = np.arange(0, counts.shape[0], 37)
+    mfs, mrs = int(m["max_family_size"]), int(m["max_root_family_size"])
+    rd = spiky_rootdist(100, 2)
+    priors = {"rootdist": ref.prior_table("rootdist", rootdist=rd)[0],
+              "poisson08": ref.prior_table("poisson", mrs, 0.8)[0],
+              "poisson12": ref.prior_table("poisson", mrs, 12.0)[0]}
+    out["mammals_sub"] = sub
+    out["mammals_rootdist_sizes"] = np.array(sorted(rd))
+    out["mammals_rootdist_counts"] = np.array([rd[k] for k in sorted(rd)])
+    for pname, prior in priors.items():
+        assert len(prior) < mrs
+        out["mammals_%s_prior" % pname] = prior
+        c = ref.ctx(str(m["newick"]), species, counts[sub], mfs, mrs, prior.astype(np.float64))
+        b = c.eval_base([0.0018])
+        g = c.eval_gamma([0.0018], m["gamma_mult"], m["gamma_probs"])
+        rg = c.reconstruct_gamma([0.0018], m["gamma_mult"], m["gamma_probs"])
+        k = "mammals_%s_" % pname
+        out[k + "ref_base"] = b["neg_lnl"]
+        out[k + "ref_family_lnl"] = b["family_lnl"]
+        out[k + "ref_gamma"] = g["neg_lnl"]
+        out[k + "ref_cat_lk"] = g["cat_lk"]
+        out[k + "ref_failed"] = g["failed"]
+        out[k + "ref_rec"] = c.reconstruct_base([0.0018])
+        out[k + "ref_rec_gamma"] = rg["states"]
+        out[k + "ref_rec_gamma_cat"] = rg["cat_states"]
+        c.close()
+        print(pname, "table", len(prior), "base", b["neg_lnl"], "gamma", g["neg_lnl"])
+    np.savez_compressed(os.path.join(OUT, "priors.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "priors":
+        make_priors()
+        return
     build_ref()
     ref = RefLib()
     ex = os.path.join(REF, "examples")

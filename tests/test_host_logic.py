@@ -89,6 +89,34 @@ def test_uniform_prior_is_float():
     assert r[0] == 0 and r[5] == np.float32(1) / np.float32(9)
 
 
+def test_prior_tables_match_the_reference_constructors(ref, golden, tmp_path):
+    """Row a12: the three priors of user_data::create_prior (src/user_data.cpp:176-206) as float32 tables, from the Python
+    restatement and from the library's C++ builders (cafe_b200_io_make_prior), against the tables the reference's own
+    root_equilibrium_distribution constructors give (ref_prior_table) -- bit for bit, including the length of the table."""
+    from cafe5_b200 import io_cpp
+    for R in (8, 45, 150, 188):
+        want = ref.prior_table("uniform", R)[0]
+        assert np.array_equal(fam.uniform_prior(R), want) and np.array_equal(io_cpp.make_prior("uniform", R), want)
+    for lam, n in ((0.8, 150), (5.3, 45), (6.5, 45), (12.0, 150), (40.0, 188), (0.05, 30)):
+        want = ref.prior_table("poisson", n, lam)[0]
+        assert np.array_equal(fam.poisson_prior(lam, n), want), (lam, n)
+        assert np.array_equal(io_cpp.make_prior("poisson", n, lam), want), (lam, n)
+    rng = np.random.default_rng(3)
+    for case in range(6):
+        rd = {int(s): int(rng.integers(1, 5000)) for s in rng.choice(np.arange(0, 120), size=int(rng.integers(1, 40)), replace=False)}
+        want = ref.prior_table("rootdist", rootdist=rd)[0]
+        assert np.array_equal(fam.rootdist_prior(rd), want)
+        path = tmp_path / ("rootdist%d.txt" % case)
+        path.write_text("".join("%d\t%d\n" % kv for kv in rd.items()))
+        assert np.array_equal(io_cpp.make_prior("rootdist", rootdist_path=path), want)
+    # the committed fixtures carry the reference's tables too (the GPU box has no reference sources)
+    g = golden["priors"]
+    assert np.array_equal(fam.poisson_prior(float(g["small_poisson_lambda"]), 45), g["small_poisson_prior"])
+    assert np.array_equal(fam.poisson_prior(0.8, 150), g["mammals_poisson08_prior"])
+    rd = dict(zip(g["mammals_rootdist_sizes"].tolist(), g["mammals_rootdist_counts"].tolist()))
+    assert np.array_equal(fam.rootdist_prior(rd), g["mammals_rootdist_prior"])
+
+
 def test_error_model_file_and_epsilon_table(tmp_path):
     p = tmp_path / "em.txt"
     p.write_text("maxcnt: 20\ncntdiff -1 0 1\n0 0.0 0.8 0.2\n1 0.2 0.6 0.2\n20 0.2 0.6 0.2\n")
