@@ -17,17 +17,19 @@ std::string& create_error()
 namespace {
 
 // ---- schedule: post-order over internal nodes, heavier subtree first, so few vectors are live ----
-void build_schedule(cafe_b200_ctx* c)
+// pseudo_leaf[v] != 0: v is a table node the pass gathers like a leaf (its subtree is not scheduled); empty = the whole tree.
+void build_schedule(const cafe_b200_ctx* c, const std::vector<char>& pseudo_leaf, Schedule& out)
 {
     const int n = c->n_nodes;
+    auto leafish = [&](int v) { return c->leaf_col[v] >= 0 || (!pseudo_leaf.empty() && pseudo_leaf[v]); };
     std::vector<std::vector<int>> kids(n);
     for (int i = n - 1; i >= 0; --i)
         if (c->parent[i] >= 0) kids[c->parent[i]].push_back(i);   // decreasing index == reference descendant order
     std::vector<int> need(n, 0);
     for (int i = 0; i < n; ++i) {                                 // children precede parents
-        if (c->leaf_col[i] >= 0) continue;
+        if (leafish(i)) continue;
         std::vector<int> sub;
-        for (int k : kids[i]) if (c->leaf_col[k] < 0) sub.push_back(need[k]);
+        for (int k : kids[i]) if (!leafish(k)) sub.push_back(need[k]);
         std::sort(sub.rbegin(), sub.rend());
         int best = 1;
         for (size_t j = 0; j < sub.size(); ++j) best = std::max(best, sub[j] + (int)j);
@@ -40,7 +42,8 @@ void build_schedule(cafe_b200_ctx* c)
     std::vector<int> state(n, 0);
     std::vector<std::vector<int>> visit(n);
     for (int i = 0; i < n; ++i) {
-        for (int k : kids[i]) if (c->leaf_col[k] < 0) visit[i].push_back(k);
+        if (leafish(i)) continue;
+        for (int k : kids[i]) if (!leafish(k)) visit[i].push_back(k);
         std::stable_sort(visit[i].begin(), visit[i].end(), [&](int a, int b) { return need[a] > need[b]; });
     }
     while (!stack.empty()) {
@@ -52,13 +55,13 @@ void build_schedule(cafe_b200_ctx* c)
     std::vector<int> slot_of(n, -1);
     std::vector<int> free_slots;
     int n_slots = 0;
-    c->steps.clear();
-    c->children.clear();
+    out.steps.clear();
+    out.children.clear();
     for (int v : order) {
         Step st{};
         st.node = v;
         st.is_root = c->parent[v] < 0;
-        st.child_begin = (int)c->children.size();
+        st.child_begin = (int)out.children.size();
         st.n_children = (int)kids[v].size();
         int s;
         if (!free_slots.empty()) { s = free_slots.back(); free_slots.pop_back(); }
@@ -69,49 +72,53 @@ void build_schedule(cafe_b200_ctx* c)
         // A two-child product is commutative bit for bit, so the contraction (internal child) goes first and the
         // leaf factor is multiplied into the accumulators in registers: no parking of the running product.
         // Three or more children keep the reference's descendant order (the association matters there).
-        if (order_kids.size() == 2 && c->leaf_col[order_kids[0]] >= 0 && c->leaf_col[order_kids[1]] < 0)
+        if (order_kids.size() == 2 && leafish(order_kids[0]) && !leafish(order_kids[1]))
             std::swap(order_kids[0], order_kids[1]);
         for (int k : order_kids) {
             StepChild ch{};
             ch.node = k;
-            ch.leaf_row = c->leaf_col[k] >= 0 ? c->leaf_row_of_node[k] : -1;
-            ch.slot = c->leaf_col[k] >= 0 ? -1 : slot_of[k];
-            c->children.push_back(ch);
+            ch.leaf_row = leafish(k) ? c->leaf_row_of_node[k] : -1;
+            ch.slot = leafish(k) ? -1 : slot_of[k];
+            out.children.push_back(ch);
         }
-        c->steps.push_back(st);
-        for (int k : kids[v]) if (c->leaf_col[k] < 0) free_slots.push_back(slot_of[k]);
+        out.steps.push_back(st);
+        for (int k : kids[v]) if (!leafish(k)) free_slots.push_back(slot_of[k]);
     }
     std::vector<int> step_of(n, -1);
-    for (size_t i = 0; i < c->steps.size(); ++i) step_of[c->steps[i].node] = (int)i;
-    for (auto& st : c->steps) st.parent_step = c->parent[st.node] < 0 ? -1 : step_of[c->parent[st.node]];
-    c->n_slots = n_slots;
+    for (size_t i = 0; i < out.steps.size(); ++i) step_of[out.steps[i].node] = (int)i;
+    for (auto& st : out.steps) st.parent_step = c->parent[st.node] < 0 ? -1 : step_of[c->parent[st.node]];
+    out.n_slots = n_slots;
 
     // ---- resident kernel: which factor travels how ----
     auto chain = [&](int v) {      // v's factor stays in registers: its parent is the very next step and has <= 2 children
-        if (c->leaf_col[v] >= 0 || c->parent[v] < 0) return false;
+        if (leafish(v) || c->parent[v] < 0) return false;
         int P = c->parent[v];
         return kids[P].size() <= 2 && step_of[P] == step_of[v] + 1;
     };
     std::vector<int> fslot_of(n, -1), free_f;
     int n_f = 0;
-    c->gemm_nodes.clear();
-    for (auto& st : c->steps) {
+    out.gemm_nodes.clear();
+    for (auto& st : out.steps) {
         const int v = st.node;
         st.carry_in = 0;
         for (int i = 0; i < st.n_children; ++i) {
-            StepChild& ch = c->children[st.child_begin + i];
+            StepChild& ch = out.children[st.child_begin + i];
             if (c->leaf_col[ch.node] >= 0) { ch.kind = 0; ch.f_slot = -1; }
+            else if (leafish(ch.node)) {                      // table node: gathered like a leaf column of its factor table
+                const TableNode& t = c->tnodes[c->tnode_of[ch.node]];
+                ch.kind = 3; ch.slot = (int32_t)t.rows_before; ch.f_slot = (int32_t)t.D;
+            }
             else if (chain(ch.node)) { ch.kind = 1; ch.f_slot = -1; st.carry_in = 1; }
             else { ch.kind = 2; ch.f_slot = fslot_of[ch.node]; }
         }
         for (int i = 0; i < st.n_children; ++i) {      // slots of consumed factors are free again
-            const StepChild& ch = c->children[st.child_begin + i];
+            const StepChild& ch = out.children[st.child_begin + i];
             if (ch.kind == 2) free_f.push_back(ch.f_slot);
         }
         st.f_slot = -1;
         if (st.is_root) st.dst_kind = 2;
         else {
-            c->gemm_nodes.push_back(v);
+            out.gemm_nodes.push_back(v);
             if (chain(v)) st.dst_kind = 0;
             else {
                 st.dst_kind = 1;
@@ -121,7 +128,151 @@ void build_schedule(cafe_b200_ctx* c)
             }
         }
     }
-    c->n_fslots = std::max(n_f, 1);
+    out.n_fslots = std::max(n_f, 1);
+}
+
+// ---- subtree-pattern tables: which nodes, their distinct patterns, the id tables (host, once per context) ----
+// counts_t: [n_leaves][U_stride] unique count table.  Appends one id row per table node the main pass gathers (counts_t grows to
+// [n_leaves + n_cut][U_stride]) and fills c->tnodes / d_ids / the schedules.  A node qualifies when every child is a leaf or a
+// table node and its distinct patterns number at most frac * U.
+void plan_tables(cafe_b200_ctx* c, std::vector<int32_t>& counts_t, int n_leaves)
+{
+    c->tables_on = false;
+    c->tnodes.clear();
+    c->tnode_of.assign(c->n_nodes, -1);
+    const char* mode = std::getenv("CAFE_B200_TABLES");
+    const bool force = mode && std::strcmp(mode, "force") == 0;
+    if (mode && std::strcmp(mode, "0") == 0) return;
+    double frac = 0.75;   // measured on the config-5 shard (B200): 0.25 -> 33.9 ms, 0.5 -> 31.2, 0.75 -> 30.1, 0.9 -> 30.7 (no tables: 61.3)
+    if (const char* e = std::getenv("CAFE_B200_TABLE_FRAC")) frac = std::atof(e);
+    if (force && !std::getenv("CAFE_B200_TABLE_FRAC")) frac = 1.0;
+    const int64_t U = c->U, US = c->U_stride;
+    if (!force && U < 8192) return;                  // small problems: the extra launches cost more than the columns they save
+    if (c->n_mtiles != 1 || !c->use_dmma || c->prune_pref < 2 || c->resident_wn != 2) return;
+    const int n = c->n_nodes;
+    std::vector<std::vector<int>> kids(n);
+    for (int i = n - 1; i >= 0; --i)
+        if (c->parent[i] >= 0) kids[c->parent[i]].push_back(i);
+    std::vector<std::vector<int32_t>> ids(n);        // per table node: pattern id of every unique family
+    std::vector<int> level(n, -1);
+    std::vector<std::vector<int32_t>> job_ids(n);    // per table node: [n_children][D_stride]
+    auto col_of = [&](int v, int64_t u) -> int32_t {
+        return c->leaf_col[v] >= 0 ? counts_t[(size_t)c->leaf_row_of_node[v] * US + u] : ids[v][u];
+    };
+    for (int v = 0; v < n - 1; ++v) {                // children precede parents; the root is never a table
+        if (c->leaf_col[v] >= 0) continue;
+        bool ok = true;
+        int lv = 0;
+        for (int k : kids[v]) {
+            if (c->leaf_col[k] >= 0) continue;
+            if (level[k] < 0) { ok = false; break; }
+            lv = std::max(lv, level[k] + 1);
+        }
+        if (!ok) continue;
+        const int m = (int)kids[v].size();
+        const int64_t limit = (int64_t)std::floor(frac * (double)U);
+        std::vector<int32_t> id(U);
+        std::vector<int32_t> first;                  // child ids of every pattern, pattern-major
+        int64_t D = 0;
+        bool over = false;
+        if (m == 2) {
+            std::unordered_map<uint64_t, int32_t> seen;
+            seen.reserve((size_t)std::min<int64_t>(U, 1 << 22));
+            for (int64_t u = 0; u < U && !over; ++u) {
+                const uint32_t a = (uint32_t)col_of(kids[v][0], u), b = (uint32_t)col_of(kids[v][1], u);
+                auto it = seen.find(((uint64_t)a << 32) | b);
+                if (it == seen.end()) {
+                    if (D >= limit) { over = true; break; }
+                    it = seen.emplace(((uint64_t)a << 32) | b, (int32_t)D).first;
+                    first.push_back((int32_t)a); first.push_back((int32_t)b);
+                    ++D;
+                }
+                id[u] = it->second;
+            }
+        } else {
+            std::unordered_map<std::string, int32_t> seen;
+            std::string key((size_t)m * sizeof(int32_t), '\0');
+            for (int64_t u = 0; u < U && !over; ++u) {
+                for (int j = 0; j < m; ++j) { const int32_t x = col_of(kids[v][j], u); memcpy(&key[(size_t)j * sizeof x], &x, sizeof x); }
+                auto it = seen.find(key);
+                if (it == seen.end()) {
+                    if (D >= limit) { over = true; break; }
+                    it = seen.emplace(key, (int32_t)D).first;
+                    for (int j = 0; j < m; ++j) first.push_back(col_of(kids[v][j], u));
+                    ++D;
+                }
+                id[u] = it->second;
+            }
+        }
+        if (over || D == 0) continue;
+        level[v] = lv;
+        ids[v] = std::move(id);
+        TableNode t;
+        t.node = v; t.level = lv; t.D = D; t.D_stride = (D + 63) / 64 * 64; t.kids = kids[v];
+        job_ids[v].assign((size_t)m * t.D_stride, 0);
+        for (int64_t d = 0; d < D; ++d)
+            for (int j = 0; j < m; ++j) job_ids[v][(size_t)j * t.D_stride + d] = first[(size_t)d * m + j];
+        c->tnodes.push_back(std::move(t));
+    }
+    if (c->tnodes.empty()) return;
+    std::stable_sort(c->tnodes.begin(), c->tnodes.end(), [](const TableNode& a, const TableNode& b) { return a.level < b.level; });
+    c->table_rows = 0;
+    c->n_table_levels = 0;
+    std::vector<int32_t> all_ids;
+    for (size_t i = 0; i < c->tnodes.size(); ++i) {
+        TableNode& t = c->tnodes[i];
+        c->tnode_of[t.node] = (int)i;
+        t.rows_before = c->table_rows;
+        c->table_rows += t.D;
+        t.ids_off = (int64_t)all_ids.size();
+        all_ids.insert(all_ids.end(), job_ids[t.node].begin(), job_ids[t.node].end());
+        c->n_table_levels = std::max(c->n_table_levels, t.level + 1);
+    }
+    if (c->table_rows * 8 > (int64_t)INT32_MAX) { c->tnodes.clear(); c->tnode_of.assign(n, -1); return; }   // row offsets are int32 in the kernel (K <= 8)
+    // the main pass gathers the table nodes whose parent is not a table: one more id row each
+    std::vector<char> pseudo(n, 0);
+    int extra = 0;
+    for (const TableNode& t : c->tnodes)
+        if (c->tnode_of[c->parent[t.node]] < 0) {
+            pseudo[t.node] = 1;
+            c->leaf_row_of_node[t.node] = n_leaves + extra++;
+        }
+    counts_t.resize((size_t)(n_leaves + extra) * US, 0);
+    for (const TableNode& t : c->tnodes)
+        if (pseudo[t.node]) std::copy(ids[t.node].begin(), ids[t.node].end(), counts_t.begin() + (size_t)c->leaf_row_of_node[t.node] * US);
+    build_schedule(c, pseudo, c->tsched_main);
+    // table launches: level by level, at most MAX_TABLE_JOBS nodes per launch; job j = step j (one step, all children gathers)
+    c->tsched_jobs.clear();
+    c->tjobs.clear();
+    for (int lv = 0; lv < c->n_table_levels; ++lv) {
+        std::vector<int> members;
+        for (size_t i = 0; i < c->tnodes.size(); ++i) if (c->tnodes[i].level == lv) members.push_back((int)i);
+        for (size_t b = 0; b < members.size(); b += MAX_TABLE_JOBS) {
+            std::vector<int> group(members.begin() + b, members.begin() + std::min(members.size(), b + MAX_TABLE_JOBS));
+            Schedule sc;
+            for (int ti : group) {
+                const TableNode& t = c->tnodes[ti];
+                Step st{};
+                st.node = t.node; st.is_root = 0; st.out_slot = 0; st.n_children = (int)t.kids.size(); st.child_begin = (int)sc.children.size();
+                st.parent_step = -1; st.carry_in = 0; st.dst_kind = 3; st.f_slot = (int32_t)t.rows_before;
+                for (size_t j = 0; j < t.kids.size(); ++j) {
+                    const int k = t.kids[j];
+                    StepChild ch{};
+                    ch.node = k; ch.leaf_row = (int32_t)j;
+                    if (c->leaf_col[k] >= 0) { ch.kind = 0; ch.slot = -1; ch.f_slot = -1; }
+                    else { const TableNode& tk = c->tnodes[c->tnode_of[k]]; ch.kind = 3; ch.slot = (int32_t)tk.rows_before; ch.f_slot = (int32_t)tk.D; }
+                    sc.children.push_back(ch);
+                }
+                sc.steps.push_back(st);
+                sc.gemm_nodes.push_back(t.node);
+            }
+            c->tsched_jobs.push_back(std::move(sc));
+            c->tjobs.push_back(std::move(group));
+        }
+    }
+    c->d_ids.reserve(std::max<size_t>(all_ids.size(), 1));
+    CK(cudaMemcpy(c->d_ids.p, all_ids.data(), all_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    c->tables_on = true;
 }
 
 void choose_tiling(cafe_b200_ctx* c)
@@ -264,21 +415,22 @@ KeyPlan plan_keys(const cafe_b200_ctx* c, const double* lambdas, const double* m
 
 namespace {
 
-void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
+// steps / children / key index / contraction nodes (and, for a table launch, its jobs) -> the kernel-parameter block
+bool fill_inline(InlineSchedule& s, const std::vector<Step>& steps, const std::vector<StepChild>& children, const std::vector<int32_t>& gemm_nodes,
+                 const KeyPlan& kp, int n_nodes, const std::vector<int32_t>* jobs = nullptr)
 {
-    InlineSchedule& s = c->sched;
-    const size_t n_steps = c->steps.size(), n_children = c->children.size();
-    const size_t words = n_steps * 9 + n_children * 5 + kp.mat_of.size() + c->gemm_nodes.size();
+    const size_t words = steps.size() * 9 + children.size() * 5 + kp.mat_of.size() + gemm_nodes.size() + (jobs ? jobs->size() : 0);
     s.valid = 0;
-    if (words > (size_t)SCHED_WORDS || kp.mat_of.size() != (kp.mat_of.size() / c->n_nodes) * (size_t)c->n_nodes) return;
+    s.n_jobs = 0; s.off_jobs = 0; s.n_job_tiles = 0; s.pad = 0;
+    if (words > (size_t)SCHED_WORDS || kp.mat_of.size() != (kp.mat_of.size() / n_nodes) * (size_t)n_nodes) return false;
     int o = 0;
-    for (const Step& st : c->steps) {
+    for (const Step& st : steps) {
         const int32_t f[9] = {st.node, st.is_root, st.out_slot, st.n_children, st.child_begin, st.parent_step, st.carry_in, st.dst_kind, st.f_slot};
         memcpy(s.w + o, f, sizeof f);
         o += 9;
     }
     s.off_children = o;
-    for (const StepChild& ch : c->children) {
+    for (const StepChild& ch : children) {
         const int32_t f[5] = {ch.node, ch.leaf_row, ch.slot, ch.kind, ch.f_slot};
         memcpy(s.w + o, f, sizeof f);
         o += 5;
@@ -287,8 +439,20 @@ void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
     memcpy(s.w + o, kp.mat_of.data(), kp.mat_of.size() * sizeof(int32_t));
     o += (int)kp.mat_of.size();
     s.off_gemm = o;
-    if (!c->gemm_nodes.empty()) memcpy(s.w + o, c->gemm_nodes.data(), c->gemm_nodes.size() * sizeof(int32_t));
+    if (!gemm_nodes.empty()) memcpy(s.w + o, gemm_nodes.data(), gemm_nodes.size() * sizeof(int32_t));
+    o += (int)gemm_nodes.size();
+    if (jobs) {
+        s.off_jobs = o;
+        s.n_jobs = (int)(jobs->size() / JOB_WORDS);
+        memcpy(s.w + o, jobs->data(), jobs->size() * sizeof(int32_t));
+    }
     s.valid = 1;
+    return true;
+}
+
+void fill_inline_schedule(cafe_b200_ctx* c, const KeyPlan& kp)
+{
+    fill_inline(c->sched, c->steps, c->children, c->gemm_nodes, kp, c->n_nodes);
 }
 
 }  // namespace
@@ -297,6 +461,7 @@ namespace cafe {
 void upload_plan(cafe_b200_ctx* c, const KeyPlan& kp)
 {
     fill_inline_schedule(c, kp);
+    c->last_kp = kp;                        // the table launches build their own kernel-parameter blocks from it
     size_t n_mats = kp.params.size();
     size_t arena = n_mats * (size_t)c->LD * c->LD;
     if (arena > c->d_arena.cap) {
@@ -343,10 +508,63 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
 
 namespace {
 
+bool tables_active(const cafe_b200_ctx* c)
+{
+    return c->tables_on && c->use_dmma && c->prune_kind == 2 && c->WN == 2 && !c->resident_probe;
+}
+
+// Subtree-pattern reuse: the factor tables level by level (JOBS build of the resident kernel, one launch per group of table nodes),
+// then the main pass over the reduced schedule.  Returns false (nothing launched) when a schedule does not fit the kernel-parameter
+// block; the caller then runs the plain pass.
+bool launch_with_tables(cafe_b200_ctx* c, const PruneParams& p)
+{
+    const int K = p.K, bn = 8 * c->TNW * 2;
+    const KeyPlan& kp = c->last_kp;
+    std::vector<InlineSchedule> launches(c->tsched_jobs.size());
+    for (size_t g = 0; g < c->tsched_jobs.size(); ++g) {
+        std::vector<int32_t> jobs;
+        int tile = 0;
+        for (int ti : c->tjobs[g]) {
+            const TableNode& t = c->tnodes[ti];
+            const int ncol = (int)((t.D + bn - 1) / bn);
+            const int32_t w[JOB_WORDS] = {tile, ncol, (int32_t)t.D, (int32_t)t.D_stride, (int32_t)(uint32_t)(t.ids_off & 0xffffffff),
+                                          (int32_t)(t.ids_off >> 32), 0, 0};
+            jobs.insert(jobs.end(), w, w + JOB_WORDS);
+            tile += ncol * K;
+        }
+        const Schedule& sc = c->tsched_jobs[g];
+        if (!fill_inline(launches[g], sc.steps, sc.children, sc.gemm_nodes, kp, c->n_nodes, &jobs)) return false;
+        launches[g].n_job_tiles = tile;
+    }
+    if (!fill_inline(c->tsched, c->tsched_main.steps, c->tsched_main.children, c->tsched_main.gemm_nodes, kp, c->n_nodes)) return false;
+    c->d_tables.reserve((size_t)c->table_rows * K * c->LD, true);
+    c->last_table_launches = 0;
+    for (size_t g = 0; g < launches.size(); ++g) {
+        PruneParams pj = p;
+        pj.counts_t = c->d_ids.p;
+        pj.tables = c->d_tables.p;
+        pj.n_steps = (int)c->tsched_jobs[g].steps.size();
+        pj.n_gemm = 1;
+        pj.n_fslots = 1;
+        const int grid = std::min(launches[g].n_job_tiles, 2 * c->n_sms);
+        CK(launch_prune_resident_wn2_tables(c->TM, c->TNW, grid, c->N, c->dmma_stages, c->stream, pj, launches[g]));
+        ++c->last_table_launches;
+    }
+    PruneParams pm = p;
+    pm.tables = c->d_tables.p;
+    pm.n_steps = (int)c->tsched_main.steps.size();
+    pm.n_gemm = (int)c->tsched_main.gemm_nodes.size();
+    pm.n_fslots = c->tsched_main.n_fslots;
+    CK(launch_prune_resident_wn2(c->TM, c->TNW, c->grid, c->N, c->dmma_stages, c->stream, pm, c->tsched));
+    return true;
+}
+
 void launch_any_prune(cafe_b200_ctx* c, PruneParams& p)
 {
+    c->last_table_launches = 0;
     if (!c->use_dmma) CK(launch_prune_dfma(c->TM, c->TN, c->grid, c->S, c->stream, p));
     else if (c->prune_kind == 2) {
+        if (tables_active(c) && launch_with_tables(c, p)) return;
         if (c->WN == 2 && c->resident_probe) {
             c->d_probe.reserve((size_t)2 * 4 * (PROBE_CHUNKS * 4 + 4));
             CK(cudaMemsetAsync(c->d_probe.p, 0, c->d_probe.cap * sizeof(int64_t), c->stream));
@@ -374,7 +592,7 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     p.logprior = c->d_logprior.p;
     p.slot_stride = (int64_t)c->n_mtiles * bm * bn;
     const bool resident = c->use_dmma && c->prune_kind == 2;
-    c->d_scratch.reserve((size_t)c->grid * (resident ? c->n_fslots : c->n_slots) * p.slot_stride);
+    c->d_scratch.reserve((size_t)c->grid * (resident ? std::max(c->n_fslots, c->tsched_main.n_fslots) : c->n_slots) * p.slot_stride);
     p.scratch = c->d_scratch.p;
     p.gemm_nodes = c->d_gemm_nodes.p;
     p.n_gemm = (int)c->gemm_nodes.size();
@@ -467,7 +685,7 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
         final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, c->d_partial_fail.p, nb, c->d_result.p);
     }
     CK(cudaGetLastError());
-    c->last_launches = c->matgen_entry ? 4 : 5;   // [pow table +] matrices, pruning, finish, final sum
+    c->last_launches = (c->matgen_entry ? 4 : 5) + c->last_table_launches;   // [pow table +] matrices, [factor tables,] pruning, finish, final sum
     c->stats_valid = true;
     return true;
 }
@@ -613,13 +831,22 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
             const int32_t* row = counts + (size_t)uniq[u] * n_species;
             for (int j = 0; j < n_leaves; ++j) counts_t[(size_t)j * c->U_stride + u] = row[c->leaf_col[leaf_nodes[j]]];
         }
+        plan_tables(c, counts_t, n_leaves);       // may append pattern-id rows for the table nodes the main pass gathers
         c->d_counts_t.reserve(counts_t.size());
         CK(cudaMemcpy(c->d_counts_t.p, counts_t.data(), counts_t.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         c->d_f2u.reserve(n_families);
         CK(cudaMemcpy(c->d_f2u.p, c->f2u.data(), (size_t)n_families * sizeof(int64_t), cudaMemcpyHostToDevice));
 
         c->d_zero.reserve(256, true);
-        build_schedule(c);
+        {
+            Schedule full;
+            build_schedule(c, std::vector<char>(), full);
+            c->steps = std::move(full.steps);
+            c->children = std::move(full.children);
+            c->gemm_nodes = std::move(full.gemm_nodes);
+            c->n_slots = full.n_slots;
+            c->n_fslots = full.n_fslots;
+        }
         c->d_steps.reserve(c->steps.size());
         CK(cudaMemcpy(c->d_steps.p, c->steps.data(), c->steps.size() * sizeof(Step), cudaMemcpyHostToDevice));
         c->d_children.reserve(c->children.size());
@@ -665,6 +892,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     c->d_partial.release(); c->d_partial_fail.release(); c->d_result.release(); c->d_roots.release();
     c->d_significant.release(); c->d_failed.release(); c->d_pupko_m.release(); c->d_states.release();
     c->d_leaf_row.release(); c->d_states_f.release(); c->d_cat_states_f.release(); c->d_avg_f.release();
+    c->d_ids.release(); c->d_tables.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -822,6 +1050,21 @@ int64_t cafe_b200_unique_families(const cafe_b200_ctx* c)
     int64_t u = 0;
     for (const cafe_b200_ctx* s : c->shards) u += s->U;   // identical families in different shards are pruned once per shard
     return u;
+}
+
+int cafe_b200_node_columns(const cafe_b200_ctx* c, int64_t* columns)
+{
+    if (!c || !columns) return CAFE_B200_ERR_ARG;
+    for (int v = 0; v < c->n_nodes; ++v) columns[v] = 0;
+    const std::vector<cafe_b200_ctx*> one{const_cast<cafe_b200_ctx*>(c)};
+    for (const cafe_b200_ctx* s : c->is_group() ? c->shards : one) {
+        const bool tab = s->tables_on && s->use_dmma && s->prune_pref >= 2 && s->resident_wn == 2 && !s->resident_probe;
+        for (int v = 0; v < s->n_nodes; ++v) {
+            if (s->leaf_col[v] >= 0) continue;
+            columns[v] += tab && s->tnode_of[v] >= 0 ? s->tnodes[s->tnode_of[v]].D : s->U;
+        }
+    }
+    return CAFE_B200_OK;
 }
 
 int32_t cafe_b200_n_devices(const cafe_b200_ctx* c) { return !c ? 0 : c->is_group() ? (int32_t)c->shards.size() : 1; }

@@ -59,6 +59,26 @@ struct DevBuf {
     }
 };
 
+// A pruning schedule over the internal nodes of the tree (post-order, children before parents).
+struct Schedule {
+    std::vector<Step> steps;
+    std::vector<StepChild> children;
+    std::vector<int32_t> gemm_nodes;       // resident kernel: node of the g-th contraction of a tile
+    int n_slots = 0, n_fslots = 1;
+};
+
+// Subtree-pattern reuse: an internal node whose subtree shows few DISTINCT patterns of leaf counts among the unique
+// families gets its factor W_v = P_v . V_v computed once per pattern (a "table"), level by level from the cherries up; the main
+// pass gathers it like a leaf column.  The reference prunes identical FAMILIES once (build_reference_list, base_model.cpp:27-51);
+// this is the same idea below the root.
+struct TableNode {
+    int node = 0, level = 0;
+    int64_t D = 0, D_stride = 0;           // distinct patterns; padded to a multiple of 64
+    int64_t rows_before = 0;               // patterns of the table nodes before this one (table row offset per category)
+    int64_t ids_off = 0;                   // this node's id table in d_ids: [n_children][D_stride] child ids of every pattern
+    std::vector<int> kids;                 // children in the reference's product order (decreasing index)
+};
+
 struct KeyPlan {
     std::vector<MatParam> params;          // one per distinct matrix key
     std::vector<int32_t> mat_of;           // [K][n_nodes]
@@ -162,7 +182,23 @@ struct cafe_b200_ctx {
     std::vector<cafe::Step> steps;
     std::vector<cafe::StepChild> children;
     int n_slots = 0;
-    std::vector<int32_t> leaf_row_of_node; // row in counts_t for leaf nodes
+    std::vector<int32_t> leaf_row_of_node; // row in counts_t for leaf nodes (and, past the leaves, for the table nodes the main pass gathers)
+
+    // subtree-pattern tables (resident wn2 kernel only; CAFE_B200_TABLES=0 disables, =force enables for any problem size)
+    bool tables_on = false;
+    std::vector<cafe::TableNode> tnodes;   // sorted by level
+    std::vector<int> tnode_of;             // node -> index in tnodes, -1
+    int n_table_levels = 0;
+    int64_t table_rows = 0;                // sum of D over the table nodes (rows per category)
+    cafe::Schedule tsched_main;            // the main pass with table nodes as pseudo-leaves
+    cafe::InlineSchedule tsched{};         // its kernel-parameter form (per evaluation: carries the key index)
+    std::vector<cafe::Schedule> tsched_jobs;   // one single-step-per-job schedule per table launch
+    std::vector<std::vector<int>> tjobs;   // table nodes (indices into tnodes) of every table launch
+    cafe::DevBuf<int32_t> d_ids;
+    cafe::DevBuf<double> d_tables;
+    cafe::KeyPlan last_kp;                 // key plan of the evaluation being launched
+    int last_table_launches = 0;
+    int64_t last_columns = 0;              // contraction columns x categories executed by the last evaluation (tables + main pass)
 
     // tiling choice
     int TM = 11, TN = 4, n_mtiles = 1, LD = 176, n_col_tiles = 0, grid = 0;

@@ -15,6 +15,8 @@ cudaError_t launch_prune_stream(int TM, int TNW, int grid, int n_stages, cudaStr
 //   wn4: one 256-thread CTA per SM, BN = 32*TNW, BK = 8;  wn2: two 128-thread CTAs per SM, BN = 16*TNW, BK = 4.
 cudaError_t launch_prune_resident_wn4(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p, const InlineSchedule& sched);
 cudaError_t launch_prune_resident_wn2(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p, const InlineSchedule& sched);
+// table build of the wn2 geometry: factor tables of the nodes listed as jobs in sched (subtree-pattern reuse)
+cudaError_t launch_prune_resident_wn2_tables(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p, const InlineSchedule& sched);
 cudaError_t launch_prune_resident_wn2probe(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p, const InlineSchedule& sched);
 // Pupko reconstruction (pupko.cuh).  threads = 512 (default geometry when TN >= 2) or 256.
 cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads);

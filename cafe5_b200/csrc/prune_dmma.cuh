@@ -72,18 +72,21 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 //   factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202; no error model: the single column P(s -> obs))
 // multiplied into (or, for the first child, copied to) the accumulators.  rows: PT + first_row + i*8 for the thread's TMW row
 // tiles; columns: col0 + col_base + j*8 + e.  Gathers of the TRANSPOSED matrix: row `obs` is contiguous in s.
+// ids_row: the observed counts of this leaf for every column (U columns; padding columns replay the last one).  The same gather
+// with em == nullptr serves a subtree-pattern table child: PT = the child's factor table, ids_row = its pattern id per column.
 template <int TMW, int TNW>
 __device__ __forceinline__ void leaf_factor_into(double (&acc)[TMW][TNW][2], bool has_acc, const PruneParams& p,
-                                                 const double* __restrict__ PT, int leaf_row, int first_row, int64_t col0, int col_base)
+                                                 const double* __restrict__ PT, const int32_t* __restrict__ ids_row, int64_t U,
+                                                 const double* __restrict__ em, int first_row, int64_t col0, int col_base)
 {
 #pragma unroll
     for (int j = 0; j < TNW; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             int64_t u = col0 + col_base + j * 8 + e;
-            if (u >= p.U) u = p.U - 1;                    // padding columns replay the last family; never written out
-            const int obs = p.counts_t[(size_t)leaf_row * p.U_stride + u];
-            if (p.em == nullptr) {
+            if (u >= U) u = U - 1;                        // padding columns replay the last family; never written out
+            const int obs = ids_row[u];
+            if (em == nullptr) {
                 const double* __restrict__ r = PT + (size_t)obs * p.LD + first_row;
 #pragma unroll
                 for (int i = 0; i < TMW; ++i) {
@@ -98,7 +101,7 @@ __device__ __forceinline__ void leaf_factor_into(double (&acc)[TMW][TNW][2], boo
                 for (int d = 0; d < 3; ++d) {
                     const int idx = obs - 1 + d;
                     const bool ok = idx >= 0 && idx < p.S;
-                    pe[d] = ok ? __ldg(p.em + er * 3 + d) : 0.0;
+                    pe[d] = ok ? __ldg(em + er * 3 + d) : 0.0;
                     r[d] = PT + (size_t)(ok ? idx : obs) * p.LD + first_row;
                 }
 #pragma unroll
@@ -158,7 +161,8 @@ prune_dmma_kernel(const PruneParams p, const int n_stages)
                     const StepChild ch = p.children[sp.child_begin + ci];
                     const double* __restrict__ PT = p.arena + (size_t)mat_of[ch.node] * p.LD * p.LD;
                     if (ch.leaf_row >= 0) {
-                        leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ch.leaf_row, m0 + row_base, col0, col_base);
+                        leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, p.counts_t + (size_t)ch.leaf_row * p.U_stride, p.U, p.em, m0 + row_base,
+                                                   col0, col_base);
                     } else {
                         // ---- internal child: acc = P[m0.., 0..S) . V_child   (matrix_cache.cpp:49-56)
                         if (has_acc) {   // park the running product in the output slot while the tiles accumulate

@@ -56,7 +56,12 @@ struct ResidentCfg {
 // MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  Co-resident CTAs drift out of phase on their own (starting
 // them half a step apart on purpose changed nothing measurable), so one CTA's leaf gathers / stores overlap the other's DMMA stream.
 // VARIANT 2 is a timing build: clock stamps around the phases of the chunk loop (tools/gpu_probe_chunks.py), not used by the product.
-template <int TMW, int TNW, int WN, int BK, int MINB, int VARIANT = 0>
+// JOBS = true is the TABLE build (subtree-pattern reuse): the launch computes the factor tables W_v = P_v . V_v of up to
+// MAX_TABLE_JOBS nodes v, each over ITS OWN distinct patterns of leaf counts (columns = patterns, not families).  Job j is step j of
+// the schedule: one step whose children are all gathers (leaves, or the tables of deeper nodes built by an earlier launch), one
+// contraction, the result stored as table rows.  The main pass (JOBS = false) then gathers a table node's factor like a leaf column
+// (StepChild::kind 3) instead of pruning the subtree again for every family: identical arithmetic per column, fewer columns.
+template <int TMW, int TNW, int WN, int BK, int MINB, int VARIANT = 0, bool JOBS = false>
 __global__ void __launch_bounds__(64 * WN, MINB)
 prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__ InlineSchedule sched)
 {
@@ -97,8 +102,10 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
     // (the 5.6 KB saved per 64-column tile is a fourth pipeline stage).
     const int swz_g = (g & 3) << 2;                   // rows this thread stores: row & 3 == g & 3
     const int swz_q = q << 2;                         // rows this thread loads as B fragments: row & 3 == q
-    const int n_tiles = p.K * p.n_col_tiles;
+    const int n_tiles = JOBS ? sched.n_job_tiles : p.K * p.n_col_tiles;
     double* const my_slots = p.scratch + (size_t)blockIdx.x * p.n_fslots * p.slot_stride;
+    auto job_word = [&](int j, int w) { return sched.w[sched.off_jobs + j * JOB_WORDS + w]; };
+    const int n_gemm = JOBS ? 1 : p.n_gemm;
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, THREADS / 32); }
@@ -113,18 +120,20 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
     constexpr int NW = THREADS / 32;
     int p_stage = 0;
     unsigned p_phase = 1;                             // parity to wait for on the empty barrier (first pass: free)
-    int p_tile = blockIdx.x, p_g = 0, p_chunk = 0, p_turn = 0;
+    int p_tile = blockIdx.x, p_g = 0, p_chunk = 0, p_turn = 0, p_job = 0;
     const double* p_PT = nullptr;
     auto p_lookup = [&]() {
-        if (p.n_gemm != 0 && p_tile < n_tiles) {
-            const int kcat = p_tile / p.n_col_tiles;
-            const int node = sched.valid ? sched.w[sched.off_gemm + p_g] : p.gemm_nodes[p_g];
+        if (n_gemm != 0 && p_tile < n_tiles) {
+            if (JOBS)
+                while (p_job + 1 < sched.n_jobs && p_tile >= job_word(p_job + 1, 0)) ++p_job;
+            const int kcat = JOBS ? (p_tile - job_word(p_job, 0)) / job_word(p_job, 1) : p_tile / p.n_col_tiles;
+            const int node = JOBS ? sched.w[p_job * 9] : sched.valid ? sched.w[sched.off_gemm + p_g] : p.gemm_nodes[p_g];
             const int mat = sched.valid ? sched.w[sched.off_mat_of + kcat * p.n_nodes + node] : p.mat_of[(size_t)kcat * p.n_nodes + node];
             p_PT = p.arena + (size_t)mat * p.LD * p.LD;
         }
     };
     auto produce_one = [&]() {
-        if (p.n_gemm == 0 || p_tile >= n_tiles) return;
+        if (n_gemm == 0 || p_tile >= n_tiles) return;
         if (warp == p_turn) {
             mbar_wait(empty_bar + p_stage, p_phase);
             if (p.LD == BMP) {                   // arena stride == smem stride: the stage is one contiguous copy
@@ -145,7 +154,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
         if (++p_stage == NS) { p_stage = 0; p_phase ^= 1u; }
         if (++p_chunk == n_chunks) {
             p_chunk = 0;
-            if (++p_g == p.n_gemm) { p_g = 0; p_tile += gridDim.x; }
+            if (++p_g == n_gemm) { p_g = 0; p_tile += gridDim.x; }
             p_lookup();
         }
     };
@@ -154,13 +163,30 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
     int c_stage = 0;
     unsigned c_phase = 0;
 
+    int c_job = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int k = tile / p.n_col_tiles;
-        const int64_t col0 = (int64_t)(tile % p.n_col_tiles) * BN;
+        int k;
+        int64_t col0, U, U_stride;
+        const int32_t* __restrict__ ids;        // [rows][U_stride] leaf counts (and pattern ids of table children) per column
+        if (JOBS) {
+            while (c_job + 1 < sched.n_jobs && tile >= job_word(c_job + 1, 0)) ++c_job;
+            const int local = tile - job_word(c_job, 0), ncol = job_word(c_job, 1);
+            k = local / ncol;
+            col0 = (int64_t)(local % ncol) * BN;
+            U = job_word(c_job, 2);
+            U_stride = job_word(c_job, 3);
+            ids = p.counts_t + (((int64_t)job_word(c_job, 5) << 32) | (uint32_t)job_word(c_job, 4));
+        } else {
+            k = tile / p.n_col_tiles;
+            col0 = (int64_t)(tile % p.n_col_tiles) * BN;
+            U = p.U;
+            U_stride = p.U_stride;
+            ids = p.counts_t;
+        }
         const int32_t* mat_of = p.mat_of + (size_t)k * p.n_nodes;
         double acc[TMW][TNW][2];
 
-        for (int st = 0; st < p.n_steps; ++st) {
+        for (int st = JOBS ? c_job : 0; st < (JOBS ? c_job + 1 : p.n_steps); ++st) {
             Step sp;
             if (sched.valid) {
                 const int o = st * 9;
@@ -177,11 +203,15 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     ch.node = sched.w[o]; ch.leaf_row = sched.w[o + 1]; ch.slot = sched.w[o + 2]; ch.kind = sched.w[o + 3]; ch.f_slot = sched.w[o + 4];
                 } else ch = p.children[sp.child_begin + ci];
                 if (ch.kind == 1) continue;                       // carried: already in acc
-                if (ch.kind == 0) {
+                if (ch.kind == 0 || ch.kind == 3) {
                     // leaf: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
+                    // subtree-pattern table (kind 3): the child's factor of pattern `id`, gathered like a leaf column of its table (no
+                    // error model: it is already inside the table)
                     const int mat = sched.valid ? sched.w[sched.off_mat_of + k * p.n_nodes + ch.node] : mat_of[ch.node];
-                    const double* __restrict__ PT = p.arena + (size_t)mat * p.LD * p.LD;
-                    leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ch.leaf_row, row_base, col0, col_base);
+                    const double* __restrict__ PT = ch.kind == 3 ? p.tables + ((size_t)ch.slot * p.K + (size_t)k * ch.f_slot) * p.LD
+                                                                 : p.arena + (size_t)mat * p.LD * p.LD;
+                    leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ids + (size_t)ch.leaf_row * U_stride, U, ch.kind == 3 ? nullptr : p.em,
+                                               row_base, col0, col_base);
                 } else {
                     // factor of an earlier sibling subtree, parked in a global slot
                     const double* __restrict__ fs = my_slots + (size_t)ch.f_slot * p.slot_stride;
@@ -214,7 +244,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
 
             // The next step's leaf counts come from DRAM (the count table is streamed once per category): pull their lines into L2 now, a
             // whole contraction ahead of the gather that needs them.
-            if (sched.valid && tid < 2) {
+            if (!JOBS && sched.valid && tid < 2) {
                 int nst = st + 1, ntile = tile;
                 if (nst == p.n_steps) { nst = 0; ntile += gridDim.x; }
                 if (ntile < n_tiles) {
@@ -275,7 +305,20 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     }
                 }
                 // ---- 4. the factor stays in registers for the parent, or is parked once in a global slot ----
-                if (sp.dst_kind == 1) {
+                if (JOBS && sp.dst_kind == 3) {
+                    // one table row per pattern: the transposed layout the gathers of the parent read
+                    double* __restrict__ tb = p.tables + ((size_t)sp.f_slot * p.K + (size_t)k * U) * p.LD;
+#pragma unroll
+                    for (int j = 0; j < TNW; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int64_t col = col0 + col_base + j * 8 + e;
+                            if (col < U) {
+#pragma unroll
+                                for (int i = 0; i < TMW; ++i) tb[(size_t)col * p.LD + row_base + i * 8] = acc[i][j][e];
+                            }
+                        }
+                } else if (sp.dst_kind == 1) {
                     double* fs = my_slots + (size_t)sp.f_slot * p.slot_stride;
 #pragma unroll
                     for (int i = 0; i < TMW; ++i)

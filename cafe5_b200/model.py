@@ -148,6 +148,12 @@ class Context:
     def unique_families(self):
         return self.lib.cafe_b200_unique_families(self.h)
 
+    def node_columns(self):
+        """columns[n_nodes]: how many columns every internal node is computed for per category (subtree-pattern tables shrink it)."""
+        out = np.zeros(self.n_nodes, dtype=np.int64)
+        self._check(self.lib.cafe_b200_node_columns(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "node_columns")
+        return out
+
     def n_devices(self):
         return self.lib.cafe_b200_n_devices(self.h)
 

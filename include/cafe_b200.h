@@ -77,6 +77,12 @@ int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t* counts, in
                            int32_t max_family_size, int32_t max_root_family_size, const int32_t* devices, int32_t n_devices,
                            cafe_b200_ctx** out);
 
+/* Work accounting for the roofline: columns[n_nodes] = the number of count-vector columns node v's vector is computed for in one
+ * category of one evaluation (0 for leaves).  The reference prunes every family (gamma model) or every distinct family (base model,
+ * build_reference_list, src/base_model.cpp:27-51) through every node; here every distinct family, and a node whose subtree shows
+ * few distinct patterns of leaf counts is computed once per PATTERN (its factor table) and gathered by the families that share it. */
+int cafe_b200_node_columns(const cafe_b200_ctx* ctx, int64_t* columns);
+
 /* Number of device shards behind a context (1 for cafe_b200_create). */
 int32_t cafe_b200_n_devices(const cafe_b200_ctx* ctx);
 
