@@ -1022,6 +1022,17 @@ int cafe_b200_fetch_result(cafe_b200_ctx* c, double* neg_lnl, int64_t* n_failed)
     } catch (const CudaError& e) { return fail(c, e); }
 }
 
+void* cafe_b200_result_device(cafe_b200_ctx* c)
+{
+    if (!c) return nullptr;
+    if (c->is_group()) return cafe_b200_result_device(c->shards[0]);
+    try {
+        CK(cudaSetDevice(c->device));
+        c->d_result.reserve(2);
+        return (void*)c->d_result.p;
+    } catch (const CudaError& e) { fail(c, e); return nullptr; }
+}
+
 void* cafe_b200_stream(cafe_b200_ctx* c) { return !c ? nullptr : c->is_group() ? (void*)c->shards[0]->stream : (void*)c->stream; }
 
 int cafe_b200_last_stats(cafe_b200_ctx* c, int32_t* n_launches, int32_t* n_matrices, float* ms_matrices, float* ms_prune)

@@ -244,6 +244,13 @@ class Context:
     def stream(self):
         return self.lib.cafe_b200_stream(self.h)
 
+    def result_device(self):
+        """Device address of the {-lnL partial, failed families} pair enqueue_eval leaves behind (cafe_b200_result_device)."""
+        ptr = self.lib.cafe_b200_result_device(self.h)
+        if not ptr:
+            raise CafeError("result_device: %s" % self.lib.cafe_b200_last_error(self.h).decode())
+        return ptr
+
     def branch_probabilities(self, lambdas, states, selected=None):
         """Per-branch change probabilities (cafe_b200_branch_probabilities): [F, n_nodes], -1 for the root / unselected families."""
         lam = _lib.as_f64(lambdas)

@@ -279,6 +279,11 @@ int cafe_b200_enqueue_eval(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_
                            const double* multipliers, const double* cat_probs, int32_t n_cat);
 int cafe_b200_fetch_result(cafe_b200_ctx* ctx, double* neg_lnl, int64_t* n_failed);
 
+/* Device address of the two doubles {-lnL partial, failed families} cafe_b200_enqueue_eval leaves behind, valid in stream order
+ * after it on cafe_b200_stream(): a multi-process host (one rank per GPU) exchanges them with a collective ENQUEUED ON THAT STREAM
+ * (bench.py: NCCL all_gather) instead of a host round trip.  Fixed for the life of the context. */
+void* cafe_b200_result_device(cafe_b200_ctx* ctx);
+
 /* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
 void* cafe_b200_stream(cafe_b200_ctx* ctx);
 
