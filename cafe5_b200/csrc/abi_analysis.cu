@@ -87,12 +87,30 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int3
     if (!c) return CAFE_B200_ERR_ARG;
     if (c->is_group()) {
         if (!states || !probs) { c->err = "bad argument"; return CAFE_B200_ERR_ARG; }
+        const size_t nn = (size_t)c->n_nodes;
+        std::vector<int32_t> st;
+        std::vector<uint8_t> sel;
+        std::vector<double> pr;
+        if (!c->order.empty()) {                 // buckets: gather the caller's rows bucket-major, scatter the results back
+            st.resize((size_t)c->F * nn);
+            pr.resize((size_t)c->F * nn);
+            if (selected) sel.resize((size_t)c->F);
+            for (int64_t p = 0; p < c->F; ++p) {
+                memcpy(&st[(size_t)p * nn], states + (size_t)c->order[p] * nn, nn * sizeof(int32_t));
+                if (selected) sel[p] = selected[c->order[p]];
+            }
+        }
+        const int32_t* st_in = st.empty() ? states : st.data();
+        const uint8_t* sel_in = !selected ? nullptr : sel.empty() ? selected : sel.data();
+        double* pr_out = pr.empty() ? probs : pr.data();
         int bad = -1;
         const int rc = c->pool->run([&](int i) {
-            const size_t b = (size_t)c->shard_begin[i], nn = (size_t)c->n_nodes;
-            return cafe_b200_branch_probabilities(c->shards[i], lambdas, n_lambda, states + b * nn, selected ? selected + b : nullptr, probs + b * nn);
+            const size_t b = (size_t)c->shard_begin[i];
+            return cafe_b200_branch_probabilities(c->shards[i], lambdas, n_lambda, st_in + b * nn, sel_in ? sel_in + b : nullptr, pr_out + b * nn);
         }, &bad);
-        if (rc != CAFE_B200_OK) c->err = c->shards[bad]->err;
+        if (rc != CAFE_B200_OK) { c->err = c->shards[bad]->err; return rc; }
+        if (!pr.empty())
+            for (int64_t p = 0; p < c->F; ++p) memcpy(probs + (size_t)c->order[p] * nn, &pr[(size_t)p * nn], nn * sizeof(double));
         return rc;
     }
     try {
@@ -131,30 +149,36 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int3
 int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues)
 {
     if (!c) return CAFE_B200_ERR_ARG;
-    if (c->is_group()) {   // every device simulates the same conditional distributions (same seed) and scores its own shard of families
-        if (!pvalues) { c->err = "bad argument"; return CAFE_B200_ERR_ARG; }
-        int bad = -1;
-        const int rc = c->pool->run([&](int i) { return cafe_b200_pvalues(c->shards[i], lambdas, n_lambda, n_sims, seed, pvalues + c->shard_begin[i]); }, &bad);
-        if (rc != CAFE_B200_OK) c->err = c->shards[bad]->err;
-        return rc;
-    }
+    cafe_b200_ctx* helper = nullptr;
     cafe_b200_ctx* sim = nullptr;
     try {
         if (!lambdas || n_lambda < c->n_lambda_classes || n_sims < 1 || !pvalues) throw CudaError{"ARG: bad argument"};
         if (!c->have_prior) throw CudaError{"STATE: set_prior must be called first"};
-        const int R = c->R, n = c->n_nodes;
+        const int R = c->R, n = c->n_nodes, mfs = c->max_family_size;
+        cafe_b200_tree t{n, c->parent.data(), c->branch_length.data(), c->leaf_col.data(), c->lambda_class.data()};
         // 1. conditional distributions: n_sims families per root size 1..R, no redraws, no error model (get_random_probabilities,
-        //    create_family: src/probability.cpp:355-375,434-447), child sizes below max_family_size
+        //    create_family: src/probability.cpp:355-375,434-447), child sizes below max_family_size.  The simulator needs the tree and
+        //    full-size matrices only: a one-family helper context (this context may be sharded, or bucketed with smaller state spaces).
         const size_t Fs = (size_t)R * n_sims;
         std::vector<int32_t> roots(Fs), sim_counts(Fs * c->n_species);
         for (int r = 0; r < R; ++r) std::fill(roots.begin() + (size_t)r * n_sims, roots.begin() + (size_t)(r + 1) * n_sims, r + 1);
-        int rc = cafe_b200_simulate(c, lambdas, n_lambda, nullptr, nullptr, 0, c->max_family_size, 0, roots.data(), (int64_t)Fs, seed,
-                                    sim_counts.data(), nullptr, nullptr, nullptr);
-        if (rc != CAFE_B200_OK) return rc;
-        // 2. their likelihood at the root size they were generated from (compute_family_probabilities, :377-432; the reference
-        //    truncates each family's state space at its largest size + max(50, size/5), we keep the full space)
-        cafe_b200_tree t{n, c->parent.data(), c->branch_length.data(), c->leaf_col.data(), c->lambda_class.data()};
-        rc = cafe_b200_create(&t, sim_counts.data(), (int64_t)Fs, c->n_species, c->max_family_size, R, c->device, &sim);
+        std::vector<int32_t> dummy((size_t)c->n_species, 1);
+        int rc = cafe_b200_create(&t, dummy.data(), 1, c->n_species, mfs, R, c->device, &helper);
+        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulator context: ") + create_error()};
+        rc = cafe_b200_simulate(helper, lambdas, n_lambda, nullptr, nullptr, 0, mfs, 0, roots.data(), (int64_t)Fs, seed, sim_counts.data(),
+                                nullptr, nullptr, nullptr);
+        if (rc != CAFE_B200_OK) throw CudaError{std::string("simulator: ") + helper->err};
+        cafe_b200_destroy(helper);
+        helper = nullptr;
+        // 2. their likelihood at the root size they were generated from (compute_family_probabilities, :377-432).  Like the reference,
+        //    every simulated family is pruned over a state space truncated at m = min(max_family_size, largest size + max(50, largest / 5))
+        //    (:394,416) -- here rounded up to the next multiple of 16 states, the row tile of the pruning kernel (bucketed contexts).
+        //    The root size r of a family is one of its sizes, so r <= m and its root row exists in its bucket.
+        std::vector<int32_t> ceilings;
+        for (int v = 63; v < mfs; v += 16) ceilings.push_back(v);
+        ceilings.push_back(mfs);
+        rc = cafe_b200_create_bucketed(&t, sim_counts.data(), (int64_t)Fs, c->n_species, mfs, R, ceilings.data(), (int32_t)ceilings.size(),
+                                       c->device, &sim);
         if (rc != CAFE_B200_OK) throw CudaError{std::string("simulated context: ") + create_error()};
         rc = cafe_b200_set_prior(sim, c->prior.data(), (int32_t)c->prior.size());
         std::vector<double> vec(Fs * R);
@@ -167,18 +191,20 @@ int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda,
             for (int i = 0; i < n_sims; ++i) cond[r][i] = vec[((size_t)r * n_sims + i) * R + r];   // index r <-> root size r+1
             std::sort(cond[r].begin(), cond[r].end());
         }
-        // 3. observed families: root vectors without the error model (compute_pvalues passes NULL, :549), then
-        //    find_best_pvalue (:513-526) over root sizes below rint(1.25 * largest count)
-        const bool had_em = c->have_em;
-        c->have_em = false;
+        // 3. observed families: root vectors without the error model (compute_pvalues passes NULL, :549) over the full state space,
+        //    then find_best_pvalue (:513-526) over root sizes below rint(1.25 * largest count)
+        const std::vector<double> em = c->em_host;
+        const int em_rows = c->em_rows, em_maxcnt = c->em_maxcnt;
+        if (!em.empty() && (rc = cafe_b200_set_error_model(c, nullptr, 0, 0)) != CAFE_B200_OK) return rc;
         vec.assign((size_t)c->F * R, 0.0);
         rc = cafe_b200_root_vectors(c, lambdas, n_lambda, 1.0, vec.data());
-        c->have_em = had_em;
+        if (!em.empty()) {
+            const int rc2 = cafe_b200_set_error_model(c, em.data(), em_rows, em_maxcnt);
+            if (rc == CAFE_B200_OK) rc = rc2;
+        }
         if (rc != CAFE_B200_OK) return rc;
         for (int64_t f = 0; f < c->F; ++f) {
-            int mx = 0;
-            for (int j = 0; j < c->n_species; ++j) mx = std::max(mx, c->counts[(size_t)f * c->n_species + j]);
-            const int limit = std::min((int)std::rint(mx * 1.25), R);
+            const int limit = std::min((int)std::rint(c->max_count[(size_t)f] * 1.25), R);
             double best = 0.0;
             for (int j = 0; j < limit; ++j) {
                 const std::vector<double>& d = cond[j];
@@ -192,6 +218,7 @@ int cafe_b200_pvalues(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda,
         }
         return CAFE_B200_OK;
     } catch (const CudaError& e) {
+        if (helper) cafe_b200_destroy(helper);
         if (sim) cafe_b200_destroy(sim);
         return fail(c, e);
     }

@@ -800,7 +800,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         // ---- families: validate, build the reference list (identical count vectors pruned once) ----
         c->F = n_families;
         c->n_species = n_species;
-        c->counts.assign(counts, counts + (size_t)n_families * n_species);
+        c->max_count.assign((size_t)n_families, 0);
         std::vector<int> leaf_nodes;
         c->leaf_row_of_node.assign(n, -1);
         for (int i = 0; i < n; ++i)
@@ -815,6 +815,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
             for (int j = 0; j < n_leaves; ++j) {
                 int32_t v = row[c->leaf_col[leaf_nodes[j]]];
                 if (v < 0 || v > max_family_size) throw CudaError{"RANGE: a count is negative or exceeds max_family_size"};
+                c->max_count[f] = std::max(c->max_count[f], v);
                 memcpy(&key[(size_t)j * sizeof(int32_t)], &v, sizeof v);
             }
             auto it = seen.find(key);
@@ -935,8 +936,9 @@ int cafe_b200_set_error_model(cafe_b200_ctx* c, const double* probs, int32_t row
     if (c->is_group()) return group::set_error_model(c, probs, rows, max_cnt);
     try {
         CK(cudaSetDevice(c->device));
-        if (!probs) { c->have_em = false; return CAFE_B200_OK; }
+        if (!probs) { c->have_em = false; c->em_host.clear(); return CAFE_B200_OK; }
         if (rows < 1) throw CudaError{"ARG: error model needs at least one row"};
+        c->em_host.assign(probs, probs + (size_t)rows * 3);
         c->d_em.reserve((size_t)rows * 3);
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaMemcpy(c->d_em.p, probs, (size_t)rows * 3 * sizeof(double), cudaMemcpyHostToDevice));
@@ -1177,7 +1179,12 @@ int32_t cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->N : 0; }
 int cafe_b200_get_matrix(cafe_b200_ctx* c, double lambda, double branch_length, double* out)
 {
     if (!c) return CAFE_B200_ERR_ARG;
-    if (c->is_group()) return cafe_b200_get_matrix(c->shards[0], lambda, branch_length, out);
+    if (c->is_group()) {
+        for (cafe_b200_ctx* s : c->shards)          // a bucket may hold a smaller state space: take a shard with the full one
+            if (s->N == c->N) return cafe_b200_get_matrix(s, lambda, branch_length, out);
+        c->err = "no bucket holds the full state space";
+        return CAFE_B200_ERR_STATE;
+    }
     try {
         if (!out) throw CudaError{"ARG: null output"};
         CK(cudaSetDevice(c->device));
@@ -1336,6 +1343,85 @@ extern "C" int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t*
     g->S = s0->S; g->R = s0->R; g->N = s0->N;
     g->branch_length = s0->branch_length;
     g->parent = s0->parent; g->leaf_col = s0->leaf_col; g->lambda_class = s0->lambda_class;
+    for (const cafe_b200_ctx* sh : g->shards) g->max_count.insert(g->max_count.end(), sh->max_count.begin(), sh->max_count.end());
+    *out = g;
+    return CAFE_B200_OK;
+}
+
+// Bucketed mode (north_star: pruning "batched over families bucketed by max family size"; SURVEY.md 7 "No truncation in inference"):
+// opt-in, labelled, never the default.  A family whose largest count is x is pruned over the states 0 .. m(x),
+// m(x) = min(max_family_size, x + max(50, x / 5)) -- the truncation the reference itself applies to the simulated families of its p-value
+// path (compute_family_probabilities, src/probability.cpp:394,416) -- rounded up to the next ceiling of `state_ceilings`; every bucket is
+// a context of its own with max_family_size = its ceiling and max_root_family_size = min(R, ceiling), all on one device, run
+// concurrently on their own streams.  Results differ from the exact path by the probability mass beyond the ceiling.
+extern "C" int cafe_b200_create_bucketed(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                                         int32_t max_family_size, int32_t max_root_family_size, const int32_t* state_ceilings,
+                                         int32_t n_ceilings, int32_t device, cafe_b200_ctx** out)
+{
+    if (out) *out = nullptr;
+    if (!tree || !counts || !out || n_families <= 0 || n_species <= 0 || !state_ceilings || n_ceilings < 1) {
+        create_error() = "null or non-positive argument";
+        return CAFE_B200_ERR_ARG;
+    }
+    std::vector<int32_t> ceil(state_ceilings, state_ceilings + n_ceilings);
+    std::sort(ceil.begin(), ceil.end());
+    while (!ceil.empty() && ceil.back() >= max_family_size) ceil.pop_back();
+    ceil.push_back(max_family_size);                               // the last bucket is the exact state space
+    if (ceil.front() < 1) { create_error() = "state ceilings must be positive"; return CAFE_B200_ERR_ARG; }
+    std::vector<std::vector<int64_t>> members(ceil.size());
+    for (int64_t f = 0; f < n_families; ++f) {
+        int32_t x = 0;
+        for (int j = 0; j < n_species; ++j) {
+            const int32_t v = counts[(size_t)f * n_species + j];
+            if (v < 0 || v > max_family_size) { create_error() = "a count is negative or exceeds max_family_size"; return CAFE_B200_ERR_RANGE; }
+            x = std::max(x, v);
+        }
+        const int32_t m = std::min(max_family_size, x + std::max(50, x / 5));
+        members[std::lower_bound(ceil.begin(), ceil.end(), m) - ceil.begin()].push_back(f);
+    }
+    cafe_b200_ctx* g = new cafe_b200_ctx();
+    std::vector<int32_t> used;
+    std::vector<int32_t> packed;
+    g->shard_begin.push_back(0);
+    for (size_t b = 0; b < ceil.size(); ++b) {
+        if (members[b].empty()) continue;
+        used.push_back(ceil[b]);
+        for (int64_t f : members[b]) {
+            g->order.push_back(f);
+            packed.insert(packed.end(), counts + (size_t)f * n_species, counts + (size_t)(f + 1) * n_species);
+        }
+        g->shard_begin.push_back((int64_t)g->order.size());
+    }
+    const int n_shards = (int)used.size();
+    g->shards.assign(n_shards, nullptr);
+    g->pool = new ShardPool(n_shards);
+    std::vector<std::string> errs(n_shards);
+    int bad = -1;
+    const int rc = g->pool->run([&](int i) {
+        const int64_t b = g->shard_begin[i], e = g->shard_begin[i + 1];
+        const int r = cafe_b200_create(tree, packed.data() + (size_t)b * n_species, e - b, n_species, used[i],
+                                       std::min(max_root_family_size, used[i]), device, &g->shards[i]);
+        if (r != CAFE_B200_OK) errs[i] = cafe_b200_last_error(nullptr);
+        return r;
+    }, &bad);
+    if (rc != CAFE_B200_OK) {
+        create_error() = "bucket with ceiling " + std::to_string(used[bad]) + ": " + errs[bad];
+        cafe_b200_destroy(g);
+        return rc;
+    }
+    const cafe_b200_ctx* s0 = g->shards[0];
+    g->device = device;
+    g->F = n_families;
+    g->n_species = n_species;
+    g->n_nodes = s0->n_nodes;
+    g->n_lambda_classes = s0->n_lambda_classes;
+    g->max_family_size = max_family_size;
+    g->S = max_family_size + 1; g->R = max_root_family_size; g->N = std::max(max_root_family_size, max_family_size) + 1;
+    g->branch_length = s0->branch_length;
+    g->parent = s0->parent; g->leaf_col = s0->leaf_col; g->lambda_class = s0->lambda_class;
+    g->max_count.resize((size_t)n_families);
+    for (int i = 0; i < n_shards; ++i)
+        for (int64_t j = 0; j < g->shards[i]->F; ++j) g->max_count[(size_t)g->order[g->shard_begin[i] + j]] = g->shards[i]->max_count[j];
     *out = g;
     return CAFE_B200_OK;
 }
@@ -1351,13 +1437,33 @@ int each(cafe_b200_ctx* g, const std::function<int(int, cafe_b200_ctx*)>& fn)
     return rc;
 }
 
-// -sum over families, shards added in device order (base_model.cpp:95, gamma_core.cpp:233); +inf when any shard rejected
+// -sum over families, shards added in shard order (base_model.cpp:95, gamma_core.cpp:233); +inf when any shard rejected
 double combine(const std::vector<double>& neg)
 {
     double total = 0.0;
     for (double v : neg) total += v;
     return total;
 }
+
+// A per-family output of the caller (width values per family).  Contiguous shards write straight into it at their offset; bucket
+// shards (g->order non-empty) write bucket-major into a scratch copy that finish() scatters back to the caller's family order.
+template <typename T>
+struct Out {
+    cafe_b200_ctx* g;
+    T* user;
+    size_t width;
+    std::vector<T> tmp;
+    Out(cafe_b200_ctx* g_, T* user_, size_t width_) : g(g_), user(user_), width(width_)
+    {
+        if (user && !g->order.empty()) tmp.resize((size_t)g->F * width);
+    }
+    T* at(int shard) { return !user ? nullptr : (tmp.empty() ? user : tmp.data()) + (size_t)g->shard_begin[shard] * width; }
+    void finish()
+    {
+        if (!user || tmp.empty()) return;
+        for (int64_t p = 0; p < g->F; ++p) memcpy(user + (size_t)g->order[p] * width, tmp.data() + (size_t)p * width, width * sizeof(T));
+    }
+};
 
 int set_prior(cafe_b200_ctx* g, const float* prior, int32_t n)
 {
@@ -1369,7 +1475,11 @@ int set_prior(cafe_b200_ctx* g, const float* prior, int32_t n)
 int set_error_model(cafe_b200_ctx* g, const double* probs, int32_t rows, int32_t max_cnt)
 {
     const int rc = each(g, [&](int, cafe_b200_ctx* s) { return cafe_b200_set_error_model(s, probs, rows, max_cnt); });
-    if (rc == CAFE_B200_OK) g->have_em = probs != nullptr;
+    if (rc == CAFE_B200_OK) {
+        g->have_em = probs != nullptr;
+        g->em_rows = rows; g->em_maxcnt = max_cnt;
+        if (probs) g->em_host.assign(probs, probs + (size_t)rows * 3); else g->em_host.clear();
+    }
     return rc;
 }
 
@@ -1377,10 +1487,9 @@ int eval_base(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double*
 {
     if (!neg_lnl) { g->err = "null argument"; return CAFE_B200_ERR_ARG; }
     std::vector<double> neg(g->shards.size(), 0.0);
-    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
-        return cafe_b200_eval_base(s, lambdas, n_lambda, &neg[i], family_lnl ? family_lnl + g->shard_begin[i] : nullptr);
-    });
-    if (rc == CAFE_B200_OK) *neg_lnl = combine(neg);
+    Out<double> fam(g, family_lnl, 1);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) { return cafe_b200_eval_base(s, lambdas, n_lambda, &neg[i], fam.at(i)); });
+    if (rc == CAFE_B200_OK) { *neg_lnl = combine(neg); fam.finish(); }
     return rc;
 }
 
@@ -1392,15 +1501,16 @@ int eval_gamma(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double
     const size_t n = g->shards.size();
     std::vector<double> neg(n, 0.0);
     std::vector<int64_t> nf(n, 0);
+    Out<double> o_cat(g, cat_lk, n_cat), o_fam(g, family_lk, 1), o_post(g, posterior, n_cat);
+    Out<uint8_t> o_sig(g, significant, n_cat), o_fail(g, failed, 1);
     const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
-        const size_t b = (size_t)g->shard_begin[i];
-        return cafe_b200_eval_gamma(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, &neg[i], cat_lk ? cat_lk + b * n_cat : nullptr,
-                                    family_lk ? family_lk + b : nullptr, posterior ? posterior + b * n_cat : nullptr,
-                                    significant ? significant + b * n_cat : nullptr, failed ? failed + b : nullptr, &nf[i]);
+        return cafe_b200_eval_gamma(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, &neg[i], o_cat.at(i), o_fam.at(i), o_post.at(i),
+                                    o_sig.at(i), o_fail.at(i), &nf[i]);
     });
     if (rc != CAFE_B200_OK) return rc;
     *neg_lnl = combine(neg);      // a shard with a failed family reports +inf, and so does the sum (gamma_core.cpp:216-225)
     if (n_failed) { *n_failed = 0; for (int64_t v : nf) *n_failed += v; }
+    o_cat.finish(); o_fam.finish(); o_post.finish(); o_sig.finish(); o_fail.finish();
     return rc;
 }
 
@@ -1436,12 +1546,30 @@ int last_stats(cafe_b200_ctx* g, int32_t* n_launches, int32_t* n_matrices, float
     return rc;
 }
 
+// out[F x R]; a bucket computes root sizes 1 .. R_b only (R_b <= R): the remaining entries are 0
 int root_vectors(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double multiplier, double* out)
 {
     if (!out) { g->err = "bad argument"; return CAFE_B200_ERR_ARG; }
-    return each(g, [&](int i, cafe_b200_ctx* s) {
-        return cafe_b200_root_vectors(s, lambdas, n_lambda, multiplier, out + (size_t)g->shard_begin[i] * s->R);
+    const size_t R = (size_t)g->R;
+    bool same = g->order.empty();
+    for (const cafe_b200_ctx* s : g->shards) same = same && s->R == g->R;
+    if (same) return each(g, [&](int i, cafe_b200_ctx* s) { return cafe_b200_root_vectors(s, lambdas, n_lambda, multiplier, out + (size_t)g->shard_begin[i] * R); });
+    std::vector<std::vector<double>> part(g->shards.size());
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+        part[i].resize((size_t)s->F * s->R);
+        return cafe_b200_root_vectors(s, lambdas, n_lambda, multiplier, part[i].data());
     });
+    if (rc != CAFE_B200_OK) return rc;
+    for (size_t i = 0; i < g->shards.size(); ++i) {
+        const size_t Rb = (size_t)g->shards[i]->R;
+        for (int64_t j = 0; j < g->shards[i]->F; ++j) {
+            const int64_t pos = g->shard_begin[i] + j;
+            double* dst = out + (size_t)(g->order.empty() ? pos : g->order[pos]) * R;
+            memcpy(dst, part[i].data() + (size_t)j * Rb, Rb * sizeof(double));
+            std::fill(dst + Rb, dst + R, 0.0);
+        }
+    }
+    return rc;
 }
 
 int reconstruct(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs, int32_t n_cat,
@@ -1449,11 +1577,13 @@ int reconstruct(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, const
 {
     if (!states) { g->err = "bad argument"; return CAFE_B200_ERR_ARG; }
     const size_t K = n_cat > 0 ? n_cat : 1, nn = (size_t)g->n_nodes;
-    return each(g, [&](int i, cafe_b200_ctx* s) {
-        const size_t b = (size_t)g->shard_begin[i];
-        return cafe_b200_reconstruct(s, lambdas, n_lambda, multipliers, cat_probs, n_cat, cat_states ? cat_states + b * K * nn : nullptr,
-                                     states + b * nn, averaged ? averaged + b * nn : nullptr);
+    Out<int32_t> o_cat(g, cat_states, K * nn), o_st(g, states, nn);
+    Out<double> o_avg(g, averaged, nn);
+    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+        return cafe_b200_reconstruct(s, lambdas, n_lambda, multipliers, cat_probs, n_cat, o_cat.at(i), o_st.at(i), o_avg.at(i));
     });
+    if (rc == CAFE_B200_OK) { o_cat.finish(); o_st.finish(); o_avg.finish(); }
+    return rc;
 }
 
 }  // namespace group

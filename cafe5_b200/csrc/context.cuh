@@ -158,6 +158,9 @@ struct cafe_b200_ctx {
     std::vector<int64_t> shard_begin;      // [n_shards + 1] first family of every shard
     cafe::ShardPool* pool = nullptr;
     bool is_group() const { return !shards.empty(); }
+    // cafe_b200_create_bucketed: the shards are BUCKETS of families by largest count (own, smaller state space each) on one device;
+    // order[shard_begin[b] + j] is the caller's index of family j of bucket b (empty: shards are contiguous blocks in caller order)
+    std::vector<int64_t> order;
 
     int device = 0;
     int n_sms = 0;
@@ -175,7 +178,7 @@ struct cafe_b200_ctx {
     // families
     int64_t F = 0, U = 0, U_stride = 0;
     int n_species = 0;
-    std::vector<int32_t> counts;           // F x n_species (host copy, for leaf states)
+    std::vector<int32_t> max_count;        // [F] largest count of every family (find_best_pvalue, src/probability.cpp:513-526)
     std::vector<int64_t> f2u;
 
     // schedule
@@ -217,6 +220,7 @@ struct cafe_b200_ctx {
     std::vector<float> prior;
     bool have_em = false;
     int em_rows = 0, em_maxcnt = 0;
+    std::vector<double> em_host;           // the rows last given to set_error_model (the p-value path switches the model off and back on)
 
     // device buffers
     cafe::DevBuf<int32_t> d_counts_t, d_mat_of, d_gemm_nodes;

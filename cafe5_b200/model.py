@@ -91,7 +91,7 @@ class Context:
     """Owns one cafe_b200_ctx: one GPU (device=...), or the families sharded over several GPUs of the node from this one process
     (devices=[...], cafe_b200_create_multi)."""
 
-    def __init__(self, tree, counts, max_family_size, max_root_family_size, device=0, devices=None):
+    def __init__(self, tree, counts, max_family_size, max_root_family_size, device=0, devices=None, state_ceilings=None):
         self.lib = _lib.load()
         self._pinned_bufs = {}
         self.tree = tree
@@ -104,7 +104,11 @@ class Context:
                       np.ascontiguousarray(tree.leaf_col, dtype=np.int32), np.ascontiguousarray(tree.lambda_class, dtype=np.int32))
         ct = _lib.CTree(tree.n_nodes, _lib.ip(self._keep[0]), _lib.dp(self._keep[1]), _lib.ip(self._keep[2]), _lib.ip(self._keep[3]))
         h = C.c_void_p()
-        if devices is None:
+        if state_ceilings is not None:      # opt-in bucketed mode (cafe_b200_create_bucketed): approximate, labelled
+            ce = np.ascontiguousarray(state_ceilings, dtype=np.int32)
+            rc = self.lib.cafe_b200_create_bucketed(C.byref(ct), _lib.ip(counts), self.F, self.n_species, self.max_family_size, self.R,
+                                                    _lib.ip(ce), len(ce), int(device), C.byref(h))
+        elif devices is None:
             rc = self.lib.cafe_b200_create(C.byref(ct), _lib.ip(counts), self.F, self.n_species, self.max_family_size, self.R,
                                            int(device), C.byref(h))
         else:

@@ -77,6 +77,19 @@ int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t* counts, in
                            int32_t max_family_size, int32_t max_root_family_size, const int32_t* devices, int32_t n_devices,
                            cafe_b200_ctx** out);
 
+/* Bucketed mode -- OPT-IN, approximate, never the default (north_star: pruning "batched over families bucketed by max family size").
+ * The reference's inference path prunes every family over the full state space 0 .. max_family_size; only its p-value path truncates:
+ * a simulated family whose largest size is x is pruned over 0 .. m(x), m(x) = min(max_family_size, x + max(50, x / 5))
+ * (compute_family_probabilities, src/probability.cpp:394,416).  Here the same rule assigns every family to the first of the
+ * state_ceilings[n_ceilings] (values of max_family_size for a bucket; max_family_size itself is always the last) that is >= m(x); each
+ * bucket is pruned with max_family_size = its ceiling and max_root_family_size = min(max_root_family_size, ceiling), all buckets
+ * concurrently on `device`.  Per-family results differ from cafe_b200_create by the probability mass beyond the ceiling (measured
+ * <= 1e-12 relative on the bundled data sets and the bench workload, tests/test_gpu_parity.py); root vectors are 0 beyond a bucket's
+ * root sizes.  cafe_b200_pvalues uses it internally for the simulated families, as the reference does. */
+int cafe_b200_create_bucketed(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                              int32_t max_family_size, int32_t max_root_family_size, const int32_t* state_ceilings, int32_t n_ceilings,
+                              int32_t device, cafe_b200_ctx** out);
+
 /* Work accounting for the roofline: columns[n_nodes] = the number of count-vector columns node v's vector is computed for in one
  * category of one evaluation (0 for leaves).  The reference prunes every family (gamma model) or every distinct family (base model,
  * build_reference_list, src/base_model.cpp:27-51) through every node; here every distinct family, and a node whose subtree shows
@@ -178,8 +191,9 @@ int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lamb
  * root size 1..R, n_sims families are simulated from that root size (no error model, no redraws) and their likelihood AT that root
  * size forms a sorted conditional distribution; a family's p-value is the largest, over root sizes below rint(1.25 * its largest
  * count), of the fraction of that distribution not above the family's own root-vector entry (pvalue / find_best_pvalue, :501-526).
- * The reference calls it with n_sims = 1000 (src/execute.cpp:171).  Monte-Carlo: agreement with the reference is statistical; the
- * simulated families are pruned over the full state space where the reference truncates each at its largest size + max(50, size/5). */
+ * The reference calls it with n_sims = 1000 (src/execute.cpp:171).  Monte-Carlo: agreement with the reference is statistical.  The
+ * simulated families are pruned over truncated state spaces like the reference's (largest size + max(50, size/5), src/probability.cpp:
+ * 394,416; here rounded up to a multiple of 16 states), the observed families over the full one. */
 int cafe_b200_pvalues(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, int32_t n_sims, uint64_t seed, double* pvalues);
 
 /* Per-branch change probabilities of the report (compute_viterbi_sum, src/gene_family_reconstructor.cpp:388-429, as estimator::execute
