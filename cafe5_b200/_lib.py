@@ -104,7 +104,7 @@ def load():
     cs = C.c_char_p
     L.cafe_b200_io_last_error.restype = cs
     L.cafe_b200_io_parse_tree.argtypes = [cs, cs, C.c_int32, c_ip, c_ip, c_dp, c_ip, c_ip, c_ip, C.c_char_p, C.c_int64]
-    L.cafe_b200_io_read_families.argtypes = [cs, C.POINTER(C.c_int64), c_ip, c_ip, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64]
+    L.cafe_b200_io_read_families.argtypes = [cs, cs, C.POINTER(C.c_int64), c_ip, c_ip, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64]
     L.cafe_b200_io_read_error_model.argtypes = [cs, c_dp, C.c_int32, c_ip, c_ip]
     L.cafe_b200_io_derive_sizes.argtypes = [c_ip, C.c_int64, c_ip, c_ip]
     L.cafe_b200_io_format_results.argtypes = [cs, C.c_double, c_dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double,

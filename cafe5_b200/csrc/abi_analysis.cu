@@ -59,6 +59,7 @@ int cafe_b200_simulate(cafe_b200_ctx* c, const double* lambdas, int32_t n_lambda
         sp.parent = d_parent.p; sp.leaf_col = d_leaf_col.p; sp.mat_of = c->d_mat_of.p; sp.cdf = d_cdf.p; sp.cat_probs = d_probs.p;
         sp.root_sizes = d_root.p; sp.sizes = d_sizes.p; sp.has = d_has.p; sp.counts = d_counts.p; sp.categories = d_cat.p;
         sp.exhausted = d_exh.p; sp.F = n_families; sp.seed = seed;
+        sp.em = c->have_em ? c->d_em.p : nullptr; sp.em_rows = c->em_rows;
         sp.n_nodes = n; sp.n_species = c->n_species; sp.K = K; sp.N = c->N; sp.max_sim = max_sim;
         sp.max_attempts = 1 + std::max(max_redraws, 0);
         simulate_kernel<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>(sp);

@@ -493,8 +493,8 @@ void launch_matrices(cafe_b200_ctx* c, int n_mats)
     CK(cudaGetLastError());
     dim3 grid((c->N + MG_S - 1) / MG_S, n_mats);
     if (rows_smem > 48 * 1024) {
-        CK(cudaFuncSetAttribute(matrix_gen_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
-        CK(cudaFuncSetAttribute(matrix_gen_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+        CK(allow_max_smem(matrix_gen_rows_kernel<true>));
+        CK(allow_max_smem(matrix_gen_rows_kernel<false>));
     }
     if (c->matgen_libexp)
         matrix_gen_rows_kernel<true><<<grid, 192, matrix_gen_rows_smem(c->N), c->stream>>>(c->d_params.p, c->d_powtab.p, n_mats, c->d_lg.p, c->N,
@@ -794,8 +794,9 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         c->R = max_root_family_size;
         c->N = std::max(max_root_family_size, max_family_size) + 1;   // base_model.cpp:65, gamma_core.cpp:185
         choose_tiling(c);
-        if (PruneCfg<13, 1>::smem_bytes(c->S) + 64 * 1024 > (size_t)prop.sharedMemPerBlockOptin)
-            throw CudaError{"RANGE: max_family_size too large for the shared-memory resident vector of the Pupko kernel"};
+        // the narrowest Pupko geometry (16 columns) must fit: M_v tile + matrix stages + the traceback states of every internal node
+        if (pupko_smem_bytes(c->TM, 1, c->S, (n - n_leaves)) > (size_t)prop.sharedMemPerBlockOptin)
+            throw CudaError{"RANGE: max_family_size (with this many internal nodes) too large for the shared memory of the Pupko kernel"};
 
         // ---- families: validate, build the reference list (identical count vectors pruned once) ----
         c->F = n_families;
@@ -1252,6 +1253,14 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         launch_matrices(c, (int)kp.params.size());
 
         choose_columns(c, K);
+        // the column tile must also fit shared memory (M_v tile + stages + traceback states of every step): narrow it until it does
+        while (c->TN > 1 && pupko_smem_bytes(c->TM, c->TN, c->S, (int)c->steps.size()) > c->smem_optin) {
+            c->TN >>= 1;
+            c->n_col_tiles = (int)((c->U + 16 * c->TN - 1) / (16 * c->TN));
+            c->grid = (int)std::min<int64_t>((int64_t)c->n_col_tiles * K, c->n_sms);
+        }
+        if (pupko_smem_bytes(c->TM, c->TN, c->S, (int)c->steps.size()) > c->smem_optin)
+            throw CudaError{"RANGE: state space too large for the shared memory of the Pupko kernel"};
         PupkoParams p{};
         const int bn = 16 * c->TN, bm = 16 * c->TM;
         p.steps = c->d_steps.p;

@@ -7,6 +7,20 @@
 
 namespace cafe {
 
+// Opt a kernel into the device's whole opt-in shared-memory range.  Always the SAME value for a given kernel: contexts on several
+// host threads (device shards, buckets) launch the same instantiation with different dynamic sizes, and a per-launch value would
+// let one thread lower the limit between another thread's attribute call and its launch.
+template <typename Kernel>
+inline cudaError_t allow_max_smem(Kernel kernel)
+{
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+}
+
 // DFMA register-tile kernel (kernels.cuh).  TM in 8..13, TN in {1,2,4}.
 cudaError_t launch_prune_dfma(int TM, int TN, int grid, int S, cudaStream_t stream, const PruneParams& p);
 // DMMA kernel streaming both operands (prune_dmma.cuh).  TNW in {1,2,4}.

@@ -241,48 +241,50 @@ pupko_kernel(const PupkoParams p)
     }
 }
 
-#ifdef CAFE_PUPKO_LAUNCH_IMPL   // tu_pupko.cu only
-template <int TM, int TN>
-inline size_t pupko_smem(int S, int n_steps)
+// dynamic shared memory of pupko_kernel<TM, TN, *>: M_v tile + matrix stages + the traceback states of every step
+inline size_t pupko_smem_bytes(int TM, int TN, int S, int n_steps)
 {
     const int kpad = (S + PRUNE_BK - 1) / PRUNE_BK * PRUNE_BK;
     const int tmp = pupko_tmp(TM);
     return sizeof(double) * ((size_t)kpad * (16 * TN + 2) + (size_t)PRUNE_STAGES * PRUNE_BK * 16 * tmp) + sizeof(int32_t) * (size_t)n_steps * 16 * TN;
 }
 
+#ifdef CAFE_PUPKO_LAUNCH_IMPL   // tu_pupko.cu only
 template <int TM, int TN>
-inline void launch_pupko_t(int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
+inline cudaError_t launch_pupko_t(int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
-    size_t smem = pupko_smem<TM, TN>(S, p.n_steps);
+    const size_t smem = pupko_smem_bytes(TM, TN, S, p.n_steps);
+    cudaError_t e;
     if (TN >= 2 && threads == 512) {
         constexpr int T = TN >= 2 ? 512 : 256;      // (TN = 1 never instantiates the 512-thread geometry)
-        cudaFuncSetAttribute(pupko_kernel<TM, TN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if ((e = allow_max_smem(pupko_kernel<TM, TN, T>)) != cudaSuccess) return e;
         pupko_kernel<TM, TN, T><<<grid, T, smem, stream>>>(p);
     } else {
-        cudaFuncSetAttribute(pupko_kernel<TM, TN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if ((e = allow_max_smem(pupko_kernel<TM, TN, 256>)) != cudaSuccess) return e;
         pupko_kernel<TM, TN, 256><<<grid, 256, smem, stream>>>(p);
     }
+    return cudaGetLastError();
 }
 
 template <int TN>
-inline void launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
+inline cudaError_t launch_pupko_tn(int TM, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
     switch (TM) {
-    case 8: launch_pupko_t<8, TN>(grid, S, stream, p, threads); break;
-    case 9: launch_pupko_t<9, TN>(grid, S, stream, p, threads); break;
-    case 10: launch_pupko_t<10, TN>(grid, S, stream, p, threads); break;
-    case 11: launch_pupko_t<11, TN>(grid, S, stream, p, threads); break;
-    case 12: launch_pupko_t<12, TN>(grid, S, stream, p, threads); break;
-    default: launch_pupko_t<13, TN>(grid, S, stream, p, threads); break;
+    case 8: return launch_pupko_t<8, TN>(grid, S, stream, p, threads);
+    case 9: return launch_pupko_t<9, TN>(grid, S, stream, p, threads);
+    case 10: return launch_pupko_t<10, TN>(grid, S, stream, p, threads);
+    case 11: return launch_pupko_t<11, TN>(grid, S, stream, p, threads);
+    case 12: return launch_pupko_t<12, TN>(grid, S, stream, p, threads);
+    default: return launch_pupko_t<13, TN>(grid, S, stream, p, threads);
     }
 }
 
-inline void launch_pupko_impl(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
+inline cudaError_t launch_pupko_impl(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
     switch (TN) {
-    case 4: launch_pupko_tn<4>(TM, grid, S, stream, p, threads); break;
-    case 2: launch_pupko_tn<2>(TM, grid, S, stream, p, threads); break;
-    default: launch_pupko_tn<1>(TM, grid, S, stream, p, threads); break;
+    case 4: return launch_pupko_tn<4>(TM, grid, S, stream, p, threads);
+    case 2: return launch_pupko_tn<2>(TM, grid, S, stream, p, threads);
+    default: return launch_pupko_tn<1>(TM, grid, S, stream, p, threads);
     }
 }
 

@@ -77,6 +77,8 @@ struct SimParams {
     int32_t* counts;             // [F][n_species]
     int32_t* categories;         // [F]
     unsigned long long* exhausted;
+    const double* em;            // [em_rows][3] error model of the context, or nullptr: leaf counts are perturbed like adjust_for_error_model
+    int32_t em_rows;
     int64_t F;
     uint64_t seed;
     int32_t n_nodes, n_species, K, N, max_sim, max_attempts;
@@ -115,6 +117,14 @@ simulate_kernel(const SimParams p)
                     if (col[(size_t)mid * p.N] > u) hi = mid; else lo = mid + 1;
                 }
                 c = lo;
+            }
+            if (p.em != nullptr && p.leaf_col[i] >= 0) {
+                // adjust_for_error_model (src/probability.cpp:478-499): one uniform draw moves the simulated leaf count down / up with
+                // the model's probabilities for that size (the reference throws beyond the model's last size; rows are clamped here)
+                const double* pr = p.em + (size_t)min(c, p.em_rows - 1) * 3;
+                const double rnd = rng.uniform();
+                if (rnd < pr[0]) c = max(c - 1, 0);
+                else if (rnd > (1 - pr[2])) c = c + 1;
             }
             p.sizes[(size_t)i * p.F + f] = c;
         }

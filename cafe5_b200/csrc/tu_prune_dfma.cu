@@ -7,7 +7,7 @@ template <int TM, int TN>
 cudaError_t go(int grid, int S, cudaStream_t stream, const PruneParams& p)
 {
     const size_t smem = PruneCfg<TM, TN>::smem_bytes(S);
-    cudaError_t e = cudaFuncSetAttribute(prune_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem(prune_kernel<TM, TN>);
     if (e != cudaSuccess) return e;
     prune_kernel<TM, TN><<<grid, PRUNE_THREADS, smem, stream>>>(p);
     return cudaGetLastError();

@@ -8,7 +8,7 @@ template <int TMW, int TNW>
 cudaError_t go(int grid, int n_stages, cudaStream_t stream, const PruneParams& p)
 {
     const size_t smem = DmmaCfg<TMW, TNW>::smem_bytes(n_stages);
-    cudaError_t e = cudaFuncSetAttribute(prune_dmma_kernel<TMW, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem(prune_dmma_kernel<TMW, TNW>);
     if (e != cudaSuccess) return e;
     prune_dmma_kernel<TMW, TNW><<<grid, PRUNE_THREADS, smem, stream>>>(p, n_stages);
     return cudaGetLastError();

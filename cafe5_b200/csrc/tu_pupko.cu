@@ -5,7 +5,6 @@
 namespace cafe {
 cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads)
 {
-    launch_pupko_impl(TM, TN, grid, S, stream, p, threads);
-    return cudaGetLastError();
+    return launch_pupko_impl(TM, TN, grid, S, stream, p, threads);
 }
 }  // namespace cafe

@@ -64,12 +64,20 @@ def fit_sharded(local_score, start, max_iterations=300, group=None):
     from .model import minimize
     n_eval = [0]
 
+    failure = []
+
     def objective(x):
         n_eval[0] += 1
-        neg, nf = local_score(list(x))
+        try:
+            neg, nf = local_score(list(x)) if not failure else (math.inf, 0)
+        except Exception as e:      # keep answering the collective: a rank that stops calling all_gather hangs every other rank
+            failure.append(e)
+            neg, nf = math.inf, 0
         total, _ = allreduce_score(neg, nf, group)
         return total
 
     x, f, it = minimize(objective, list(start), max_iterations)
+    if failure:
+        raise failure[0]
     # status as cafe_b200_fit reports it: 0 converged (tolx and tolf 1e-6), 2 stopped at the iteration cap
     return dict(values=x, neg_lnl=f, iterations=it, evaluations=n_eval[0], status=2 if it >= max_iterations else 0)

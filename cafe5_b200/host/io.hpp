@@ -180,7 +180,10 @@ inline std::string strip_cr(std::string s) { while (!s.empty() && s.back() == '\
 
 // CAFE format: "Desc<TAB>Family ID<TAB>sp1..." header, rows "desc<TAB>id<TAB>c1..."; CAFExp format: "#taxon" header lines, rows of
 // counts with the id in the last column (src/io.cpp:134-217).  Counts go through atoi, blank lines are skipped.
-inline FamilyTable read_gene_families(std::istream& in)
+// tree (optional): in the CAFExp format the reference looks every "#name" up in the tree, advances the column index for each of
+// them but records a column only for LEAVES (src/io.cpp:153-161) -- interior-node columns are skipped -- and rejects a name that is
+// not in the tree.  Without a tree every "#name" line is taken as a species column.
+inline FamilyTable read_gene_families(std::istream& in, const Tree* tree = nullptr)
 {
     FamilyTable ft;
     std::map<int, std::string> leaf_cols;
@@ -192,8 +195,18 @@ inline FamilyTable read_gene_families(std::istream& in)
         const std::vector<std::string> tok = split_tabs(line);
         if (!leaf_cols.empty() && line[0] != '#') header = false;
         if (header) {
-            if (line[0] == '#') leaf_cols[index++] = strip_cr(line.substr(1));
-            else {
+            if (line[0] == '#') {
+                const std::string taxon = strip_cr(line.substr(1));
+                bool keep = true;
+                if (tree) {
+                    int found = -1;
+                    for (int i = 0; i < tree->n_nodes() && found < 0; ++i) if (tree->name[i] == taxon) found = i;
+                    if (found < 0) throw std::runtime_error(taxon + " not located in tree");
+                    keep = tree->is_leaf[found] != 0;
+                }
+                if (keep) leaf_cols[index] = taxon;
+                index++;
+            } else {
                 header = false;
                 if (leaf_cols.empty())
                     for (size_t i = 2; i < tok.size(); ++i) ft.species.push_back(strip_cr(tok[i]));

@@ -55,13 +55,17 @@ int cafe_b200_io_parse_tree(const char* newick, const char* lambda_newick, int32
     } catch (const std::exception& e) { g_io_error = e.what(); return CAFE_B200_ERR_ARG; }
 }
 
-int cafe_b200_io_read_families(const char* path, int64_t* n_families, int32_t* n_species, int32_t* counts, int64_t counts_cap,
-                               char* species, int64_t species_cap, char* ids, int64_t ids_cap)
+int cafe_b200_io_read_families(const char* path, const char* newick, int64_t* n_families, int32_t* n_species, int32_t* counts,
+                               int64_t counts_cap, char* species, int64_t species_cap, char* ids, int64_t ids_cap)
 {
     try {
+        if (!path) throw std::runtime_error("null path");
         std::ifstream in(path);
-        if (!in) throw std::runtime_error(std::string("cannot open ") + (path ? path : "(null)"));
-        const cafe_b200_host::FamilyTable ft = cafe_b200_host::read_gene_families(in);
+        if (!in) throw std::runtime_error(std::string("cannot open ") + path);
+        cafe_b200_host::Tree tree;
+        const bool have_tree = newick && *newick;
+        if (have_tree) tree = cafe_b200_host::parse_newick(newick, "");
+        const cafe_b200_host::FamilyTable ft = cafe_b200_host::read_gene_families(in, have_tree ? &tree : nullptr);
         if (n_families) *n_families = (int64_t)ft.n_families();
         if (n_species) *n_species = (int32_t)ft.species.size();
         if (counts) {
@@ -77,8 +81,9 @@ int cafe_b200_io_read_families(const char* path, int64_t* n_families, int32_t* n
 int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_cap, int32_t* rows, int32_t* max_count)
 {
     try {
+        if (!path) throw std::runtime_error("null path");
         std::ifstream in(path);
-        if (!in) throw std::runtime_error(std::string("cannot open ") + (path ? path : "(null)"));
+        if (!in) throw std::runtime_error(std::string("cannot open ") + path);
         const cafe_b200_host::ErrorModelTable em = cafe_b200_host::read_error_model(in);
         if (rows) *rows = em.rows();
         if (max_count) *max_count = em.max_count;

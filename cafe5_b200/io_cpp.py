@@ -32,15 +32,16 @@ def parse_tree(newick, lambda_newick=None, capacity=8192):
                 n_lambda=nl.value, names=buf.value.decode().split("\t"))
 
 
-def read_gene_families(path):
-    """(species, ids, counts[F, n_species] int32)."""
+def read_gene_families(path, newick=None):
+    """(species, ids, counts[F, n_species] int32).  newick: the species tree; with it the CAFExp header keeps only leaf columns."""
     L = _lib.load()
     nf, ns = C.c_int64(), C.c_int32()
-    _check(L, L.cafe_b200_io_read_families(str(path).encode(), C.byref(nf), C.byref(ns), None, 0, None, 0, None, 0))
+    nw = None if not newick else newick.encode()
+    _check(L, L.cafe_b200_io_read_families(str(path).encode(), nw, C.byref(nf), C.byref(ns), None, 0, None, 0, None, 0))
     counts = np.zeros((nf.value, ns.value), dtype=np.int32)
     sp = C.create_string_buffer(1 << 20)
     ids = C.create_string_buffer(max(1 << 20, 64 * nf.value))
-    _check(L, L.cafe_b200_io_read_families(str(path).encode(), C.byref(nf), C.byref(ns), _lib.ip(counts), counts.size, sp, len(sp), ids, len(ids)))
+    _check(L, L.cafe_b200_io_read_families(str(path).encode(), nw, C.byref(nf), C.byref(ns), _lib.ip(counts), counts.size, sp, len(sp), ids, len(ids)))
     return sp.value.decode().split("\t"), ids.value.decode().split("\t"), counts
 
 

@@ -87,6 +87,19 @@ class error_model:
         self.replace_epsilons({eps[0]: new_epsilon})
 
 
+class _PinnedBlock:
+    """One cafe_b200_host_alloc block, released when the last array viewing it is garbage-collected."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.cafe_b200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
 class Context:
     """Owns one cafe_b200_ctx: one GPU (device=...), or the families sharded over several GPUs of the node from this one process
     (devices=[...], cafe_b200_create_multi)."""
@@ -124,8 +137,7 @@ class Context:
         if getattr(self, "h", None):
             self.lib.cafe_b200_destroy(self.h)
             self.h = None
-        for _, ptr in getattr(self, "_pinned_bufs", {}).values():
-            self.lib.cafe_b200_host_free(ptr)
+        # the page-locked blocks are freed when the LAST array viewing them dies (a result kept past close() stays valid)
         self._pinned_bufs = {}
 
     def __del__(self):
@@ -179,6 +191,7 @@ class Context:
             ptr = C.c_void_p()
             self._check(self.lib.cafe_b200_host_alloc(nbytes, C.byref(ptr)), "host_alloc")
             raw = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+            raw._owner = _PinnedBlock(self.lib, ptr)      # numpy keeps `raw` alive through the array's base; `raw` keeps the block
             buf = (np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape), ptr)
             self._pinned_bufs[key] = buf
         return buf[0]
@@ -206,6 +219,11 @@ class Context:
                                                   C.byref(nf)), "eval_gamma")
         out["neg_lnl"] = neg.value
         out["n_failed"] = nf.value
+        if want_family and pinned and math.isinf(neg.value) and nf.value == 0:
+            # rejected before any kernel ran (invalid lambda / alpha / saturated): the reused buffers still hold the previous call's
+            # values; hand back zeros like the fresh-array path does
+            for key in ("cat_lk", "family_lk", "posterior", "significant", "failed"):
+                out[key][...] = 0
         return out
 
     def reconstruct(self, lambdas, multipliers=None, cat_probs=None, want_cat_states=True, want_averaged=True):
@@ -332,11 +350,26 @@ def minimize(fn, x0, max_iterations=300):
     """The library's simplex search (cafe5_b200/host/nelder_mead.hpp) over a Python objective: (x, f, iterations)."""
     lib = _lib.load()
     n = len(x0)
-    cb = _lib.OBJECTIVE(lambda x, _u: float(fn([x[i] for i in range(n)])))
+    raised = []
+
+    def guarded(x, _u):
+        # ctypes prints and swallows an exception raised inside a callback and hands 0.0 to the caller -- the best score the search
+        # has ever seen.  Keep the first exception, answer +inf (a rejected point) from then on, and re-raise after the search.
+        if raised:
+            return math.inf
+        try:
+            return float(fn([x[i] for i in range(n)]))
+        except BaseException as e:      # noqa: BLE001 -- re-raised below
+            raised.append(e)
+            return math.inf
+
+    cb = _lib.OBJECTIVE(guarded)
     x0 = _lib.as_f64(x0)
     out = np.zeros(n)
     f, it = C.c_double(), C.c_int32()
     rc = lib.cafe_b200_minimize(cb, None, n, _lib.dp(x0), int(max_iterations), _lib.dp(out), C.byref(f), C.byref(it))
+    if raised:
+        raise raised[0]
     if rc:
         raise CafeError("minimize: bad argument")
     return out, f.value, it.value

@@ -182,7 +182,11 @@ int cafe_b200_fit(cafe_b200_ctx* ctx, const cafe_b200_fit_options* options, cafe
  * max_family_size, 120 by default); n_cat > 0: each family first picks a rate category with cat_probs (gamma_core.cpp:91-95).
  * counts[F x n_species] (the context's species columns); node_sizes[F x n_nodes] and categories[F] optional; n_not_at_root:
  * families still absent at the root after 50 redraws (kept, as the reference keeps them with a warning).  Counter-based RNG
- * (Philox4x32-10 keyed by seed, one stream per family): reproducible per seed, distributional parity with the reference. */
+ * (Philox4x32-10 keyed by seed, one stream per family): reproducible per seed, distributional parity with the reference.
+ * When the context holds an error model (cafe_b200_set_error_model) every simulated LEAF count is perturbed like
+ * adjust_for_error_model (src/probability.cpp:478-499), as simulator::create_trial does with the user's error model; a perturbed count
+ * may reach max_sim.  Every family draws its own rate category: the reference draws one per batch of LAMBDA_PERTURBATION_STEP_SIZE
+ * families (src/simulator.cpp:74-90), and that constant is 1 in its build (CMakeLists.txt:15). */
 int cafe_b200_simulate(cafe_b200_ctx* ctx, const double* lambdas, int32_t n_lambda, const double* multipliers, const double* cat_probs,
                        int32_t n_cat, int32_t max_sim, int32_t max_redraws, const int32_t* root_sizes, int64_t n_families, uint64_t seed,
                        int32_t* counts, int32_t* node_sizes, int32_t* categories, int64_t* n_not_at_root);
@@ -212,9 +216,11 @@ const char* cafe_b200_io_last_error(void);
 int cafe_b200_io_parse_tree(const char* newick, const char* lambda_newick, int32_t capacity, int32_t* n_nodes, int32_t* parent,
                             double* branch_length, int32_t* is_leaf, int32_t* lambda_class, int32_t* n_lambda, char* names, int64_t names_cap);
 
-/* Gene-family table, CAFE or CAFExp header style (src/io.cpp:134-217): counts[n_families x n_species]. */
-int cafe_b200_io_read_families(const char* path, int64_t* n_families, int32_t* n_species, int32_t* counts, int64_t counts_cap,
-                               char* species, int64_t species_cap, char* ids, int64_t ids_cap);
+/* Gene-family table, CAFE or CAFExp header style (src/io.cpp:134-217): counts[n_families x n_species].  newick (NULL or "": none): the
+ * species tree; in the CAFExp format the reference looks every "#name" header line up in the tree and keeps a column only for leaves
+ * (interior-node columns are skipped, unknown names rejected, src/io.cpp:153-161). */
+int cafe_b200_io_read_families(const char* path, const char* newick, int64_t* n_families, int32_t* n_species, int32_t* counts,
+                               int64_t counts_cap, char* species, int64_t species_cap, char* ids, int64_t ids_cap);
 
 /* Error-model file (src/io.cpp:228-274, src/error_model.cpp:31-50): probs[rows x 3]. */
 int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_cap, int32_t* rows, int32_t* max_count);

@@ -79,6 +79,23 @@ def test_cpp_family_reader_both_header_styles(tmp_path, ref):
         empty = tmp_path / "empty.txt"
         empty.write_text("Desc\tFamily ID\tA\tB\n")
         io_cpp.read_gene_families(empty)
+    # CAFExp header naming INTERIOR nodes too (src/io.cpp:153-161): every '#name' advances the column index, only leaves get a column;
+    # a name that is not in the tree is rejected
+    mixed = tmp_path / "cafexp_interior.txt"
+    mixed.write_text("#A\n#AB\n#B\n#C\n#CD\n#D\n5\t99\t10\t2\t77\t6\tfam1\n1\t98\t0\t3\t76\t7\tfam2\n")
+    species, ids, counts = io_cpp.read_gene_families(mixed, newick)
+    assert species == ["A", "B", "C", "D"] and ids == ["fam1", "fam2"] and counts.tolist() == [[5, 10, 2, 6], [1, 0, 3, 7]]
+    rids, rcounts = ref.read_families(mixed, newick)
+    t = io_cpp.parse_tree(newick)
+    leaves = [n for n, leaf in zip(t["names"], t["is_leaf"]) if leaf]
+    assert ids == rids and np.array_equal(counts[:, [species.index(n) for n in leaves]], rcounts)
+    assert io_cpp.derive_sizes(counts) == fam.derive_sizes(counts)          # 99 / 98 never reach the size derivation
+    unknown = tmp_path / "cafexp_unknown.txt"
+    unknown.write_text("#A\n#Z\n5\t1\tfam1\n")
+    with pytest.raises(io_cpp.IoError, match="Z not located in tree"):
+        io_cpp.read_gene_families(unknown, newick)
+    with pytest.raises(io_cpp.IoError):
+        io_cpp.read_error_model(tmp_path / "does_not_exist.txt")
 
 
 @needs_files
