@@ -294,11 +294,11 @@ void choose_tiling(cafe_b200_ctx* c)
 
 // shared-memory footprint of prune_resident_kernel<TM, TNW, WN, BK> (ResidentCfg::smem_bytes, prune_resident.cuh)
 size_t resident_stage_bytes(int tm, int bk) { return sizeof(double) * (size_t)bk * (16 * tm + 4); }
-size_t resident_fixed_bytes(int tnw, int wn, int N)
+size_t resident_fixed_bytes(int tm, int tnw, int wn)
 {
-    const int bn = 8 * tnw * wn, vrows = (N + 7) / 8 * 8;
+    const int bn = 8 * tnw * wn;
     const int parts = std::min(64 * wn / bn, 2);
-    return sizeof(double) * ((size_t)vrows * bn + 2 * parts * bn + 2 * 8);
+    return sizeof(double) * ((size_t)bn * (16 * tm + 4) + 2 * parts * bn + 2 * 8 + 2);
 }
 
 // DMMA kernels: pick the variant and its column tile.  Wide tiles amortise matrix traffic, narrow tiles fill the SMs.
@@ -323,7 +323,7 @@ int choose_columns_dmma(cafe_b200_ctx* c, int K)
                 tnw >>= 1;
             }
             if (const char* e = std::getenv("CAFE_B200_TNW")) { const int v = std::atoi(e); if (v >= 1 && v <= 4) tnw = v; }   // experiment knob
-            const size_t fixed = resident_fixed_bytes(tnw, wn, c->N), stage = resident_stage_bytes(c->TM, bk);
+            const size_t fixed = resident_fixed_bytes(c->TM, tnw, wn), stage = resident_stage_bytes(c->TM, bk);
             if (fixed + 2 * stage > avail) continue;
             int stages = (int)std::min<size_t>((avail - fixed) / stage, 8);
             if (const char* e = std::getenv("CAFE_B200_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));

@@ -31,26 +31,28 @@ namespace cafe {
 
 // Geometry: 2 x WN warps (rows x columns); warp tile (8*TMW) x (8*TNW); CTA tile BM = 16*TMW rows x BN = 8*TNW*WN columns.
 //   WN = 2 (default): 128-thread CTAs with BN = 64 and ~113 KB of shared memory, so TWO CTAs ARE RESIDENT PER SM and one CTA's leaf
-//           gathers / Vres stores / epilogue overlap the other's DMMA stream (same registers per thread and accumulators per warp
-//           as WN = 4).  Tensor pipe 77 % active (profiles/r01_prune_resident2_ncu.txt).
-//   WN = 4: one 256-thread CTA per SM, BN = 128; used when two CTAs do not fit.  Every non-contraction phase idles the tensor
-//           pipe: 69 % active in profiles/r01_prune_resident_ncu.txt.
+//           gathers / epilogue overlap the other's DMMA stream (same registers per thread and accumulators per warp as WN = 4).
+//   WN = 4: one 256-thread CTA per SM, BN = 128; used when two CTAs do not fit.
+// The resident vector V_v is kept COLUMN-MAJOR, VT[column][state] with a column stride of BMP = BM + 4 doubles:
+//   * BMP == 4 (mod 16) doubles, so the DMMA B fragments (8 columns x 4 consecutive states per warp) touch every bank pair exactly
+//     twice: two wavefronts for 32 x 8 bytes, the minimum -- no swizzle, no padding columns;
+//   * BMP is the row stride of the matrix arena and of the factor tables, so the factor of a gathered child (a leaf's matrix row
+//     P(. -> count), or a table row) is ONE contiguous 16-byte-aligned cp.async.bulk per column straight into VT[column]: the gather
+//     of the last child of a node no longer goes through registers (88 dependent 8-byte loads per thread in batches the register
+//     file allows) but through the copy engine, in flight while the other children's factors are loaded; the running product is
+//     then multiplied into VT in place, every thread touching only the elements it owns (no barrier between product and store).
 template <int TMW, int TNW, int WN, int BK>
 struct ResidentCfg {
     static constexpr int THREADS = 64 * WN;
     static constexpr int BM = 16 * TMW;
     static constexpr int BN = 8 * TNW * WN;
     static constexpr int BMP = BM + 4;
-    static constexpr int BNP = BN;                 // no padding: columns are XOR-swizzled by (row & 3) << 2 instead
+    static constexpr int VT_DOUBLES = BN * BMP;
     static constexpr int STAGE_DOUBLES = BK * BMP;
     static constexpr int MAX_STAGES = 8;
     static constexpr int PARTS = THREADS / BN < 2 ? THREADS / BN : 2;   // epilogue threads per column
-    static constexpr int TAIL_DOUBLES = 2 * PARTS * BN + 2 * MAX_STAGES;
-    static int vrows(int N) { return (N + 7) / 8 * 8; }   // child states [0, S) for the contraction, root rows [1, R] for the epilogue
-    static size_t smem_bytes(int N, int n_stages)
-    {
-        return sizeof(double) * ((size_t)vrows(N) * BNP + (size_t)n_stages * STAGE_DOUBLES + TAIL_DOUBLES);
-    }
+    static constexpr int TAIL_DOUBLES = 2 * PARTS * BN + 2 * MAX_STAGES + 2;
+    static size_t smem_bytes(int n_stages) { return sizeof(double) * ((size_t)VT_DOUBLES + (size_t)n_stages * STAGE_DOUBLES + TAIL_DOUBLES); }
 };
 
 // MINB = CTAs resident per SM (register cap 65536 / (64*WN*MINB)).  Co-resident CTAs drift out of phase on their own (starting
@@ -77,19 +79,20 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
         probe_out += 4;
     }
     using Cfg = ResidentCfg<TMW, TNW, WN, BK>;
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, BNP = Cfg::BNP, THREADS = Cfg::THREADS;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BMP = Cfg::BMP, THREADS = Cfg::THREADS;
     // Where warp 0 refills the ring: before its own chunk (one more chunk of lead, but it first waits for the slowest warp) or after it.
     // Measured on B200: "after" wins with one warp per sub-partition and CTA (WN = 2), "before" with two.
     constexpr bool PRODUCE_FIRST = WN != 2;
     extern __shared__ __align__(128) double smem_rs[];
     const int kpad = (p.S + BK - 1) / BK * BK;
     const int n_chunks = kpad / BK;
-    const int vrows = (p.N + 7) / 8 * 8;
-    double* const Vres = smem_rs;                                     // [vrows][BNP]
-    double* const stages = Vres + (size_t)vrows * BNP;                // [NS][BK][BMP]
+    double* const VT = smem_rs;                                       // [BN][BMP]: V_v, column-major
+    double* const stages = VT + Cfg::VT_DOUBLES;                      // [NS][BK][BMP]
     double* const red = stages + (size_t)NS * Cfg::STAGE_DOUBLES;     // [2][PARTS*BN]
     uint64_t* const full_bar = reinterpret_cast<uint64_t*>(red + 2 * Cfg::PARTS * BN);
     uint64_t* const empty_bar = full_bar + Cfg::MAX_STAGES;
+    uint64_t* const v_full = empty_bar + Cfg::MAX_STAGES;             // the staged child's BN bulk copies have landed in VT
+    uint64_t* const v_free = v_full + 1;                              // every warp is done reading VT (contraction / epilogue of the step before)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -97,11 +100,6 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
     const int g = lane >> 2, q = lane & 3;            // DMMA fragment coordinates
     const int row_base = wm * 8 * TMW + g;            // + i*8
     const int col_base = wn * 8 * TNW + 2 * q;        // + j*8 + e
-    // Vres swizzle: element (row, col) lives at column col ^ ((row & 3) << 2).  Rows are a multiple of 16 doubles, so unswizzled the
-    // four k-rows of a DMMA B fragment would hit the same banks; the XOR spreads them over the 32 banks without padding columns
-    // (the 5.6 KB saved per 64-column tile is a fourth pipeline stage).
-    const int swz_g = (g & 3) << 2;                   // rows this thread stores: row & 3 == g & 3
-    const int swz_q = q << 2;                         // rows this thread loads as B fragments: row & 3 == q
     const int n_tiles = JOBS ? sched.n_job_tiles : p.K * p.n_col_tiles;
     double* const my_slots = p.scratch + (size_t)blockIdx.x * p.n_fslots * p.slot_stride;
     auto job_word = [&](int j, int w) { return sched.w[sched.off_jobs + j * JOB_WORDS + w]; };
@@ -109,6 +107,8 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, THREADS / 32); }
+        mbar_init(v_full, BN);
+        mbar_init(v_free, THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -162,6 +162,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
     for (int s = 0; s < NS - 1; ++s) produce_one();
     int c_stage = 0;
     unsigned c_phase = 0;
+    unsigned free_phase = 0, vfull_phase = 0;         // parities of v_free (one phase per step) and v_full (one per staged step)
 
     int c_job = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -194,24 +195,48 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                 sp.child_begin = sched.w[o + 4]; sp.parent_step = sched.w[o + 5]; sp.carry_in = sched.w[o + 6];
                 sp.dst_kind = sched.w[o + 7]; sp.f_slot = sched.w[o + 8];
             } else sp = p.steps[st];
-            bool has_acc = sp.carry_in != 0;
-            // ---- 1. V_v = product of the children's factors (probability.cpp:215-217, 229-231) ----
-            for (int ci = 0; ci < sp.n_children; ++ci) {
+            auto child_at = [&](int ci) {
                 StepChild ch;
                 if (sched.valid) {
                     const int o = sched.off_children + (sp.child_begin + ci) * 5;
                     ch.node = sched.w[o]; ch.leaf_row = sched.w[o + 1]; ch.slot = sched.w[o + 2]; ch.kind = sched.w[o + 3]; ch.f_slot = sched.w[o + 4];
                 } else ch = p.children[sp.child_begin + ci];
+                return ch;
+            };
+            auto gather_base = [&](const StepChild& ch) -> const double* {     // row 0 of the child's gather source (matrix or table)
+                const int mat = sched.valid ? sched.w[sched.off_mat_of + k * p.n_nodes + ch.node] : mat_of[ch.node];
+                return ch.kind == 3 ? p.tables + ((size_t)ch.slot * p.K + (size_t)k * ch.f_slot) * p.LD : p.arena + (size_t)mat * p.LD * p.LD;
+            };
+            // The LAST child of the product goes through the copy engine when it is a plain column gather (a leaf without an error model,
+            // or a table node).  Products are formed in the schedule's child order either way (probability.cpp:215-217, 229-231).
+            bool staged = false;
+            StepChild sch{};
+            if (sp.n_children > 0) {
+                sch = child_at(sp.n_children - 1);
+                staged = sch.kind == 3 || (sch.kind == 0 && p.em == nullptr);
+            }
+            int staged_id = 0;
+            if (staged && tid < BN) {
+                int64_t u = col0 + tid;
+                if (u >= U) u = U - 1;                            // padding columns replay the last family; never written out
+                staged_id = ids[(size_t)sch.leaf_row * U_stride + u];
+            }
+            // this warp no longer reads VT (previous contraction / epilogue): generic-proxy accesses before, async-proxy writes after
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v_free);
+
+            bool has_acc = sp.carry_in != 0;
+            // ---- 1. the factors of the other children, through registers ----
+            for (int ci = 0; ci < sp.n_children - (staged ? 1 : 0); ++ci) {
+                const StepChild ch = child_at(ci);
                 if (ch.kind == 1) continue;                       // carried: already in acc
                 if (ch.kind == 0 || ch.kind == 3) {
                     // leaf: factor[s] = sum_d em[obs][d] * P(s -> obs-1+d)   (probability.cpp:187-202)
                     // subtree-pattern table (kind 3): the child's factor of pattern `id`, gathered like a leaf column of its table (no
                     // error model: it is already inside the table)
-                    const int mat = sched.valid ? sched.w[sched.off_mat_of + k * p.n_nodes + ch.node] : mat_of[ch.node];
-                    const double* __restrict__ PT = ch.kind == 3 ? p.tables + ((size_t)ch.slot * p.K + (size_t)k * ch.f_slot) * p.LD
-                                                                 : p.arena + (size_t)mat * p.LD * p.LD;
-                    leaf_factor_into<TMW, TNW>(acc, has_acc, p, PT, ids + (size_t)ch.leaf_row * U_stride, U, ch.kind == 3 ? nullptr : p.em,
-                                               row_base, col0, col_base);
+                    leaf_factor_into<TMW, TNW>(acc, has_acc, p, gather_base(ch), ids + (size_t)ch.leaf_row * U_stride, U,
+                                               ch.kind == 3 ? nullptr : p.em, row_base, col0, col_base);
                 } else {
                     // factor of an earlier sibling subtree, parked in a global slot
                     const double* __restrict__ fs = my_slots + (size_t)ch.f_slot * p.slot_stride;
@@ -227,19 +252,36 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                 has_acc = true;
             }
 
-            // ---- 2. V_v -> shared memory (states >= S do not exist: zero rows, the matrix rows there may be real) ----
-            __syncthreads();          // every warp finished reading Vres in the previous contraction / epilogue
-#pragma unroll
-            for (int i = 0; i < TMW; ++i) {
-                const int row = row_base + i * 8;
-                if (row < vrows) {
-                    const bool live = sp.is_root || row < p.S;
-#pragma unroll
-                    for (int j = 0; j < TNW; ++j)
-                        *reinterpret_cast<double2*>(Vres + (size_t)row * BNP + ((col_base + j * 8) ^ swz_g)) =
-                            live ? make_double2(acc[i][j][0], acc[i][j][1]) : make_double2(0.0, 0.0);
+            // ---- 2. V_v -> VT.  Everyone waits until every warp has left the previous contraction; the staged child's columns are
+            // then copied in by the copy engine (one 16-byte-aligned bulk copy of BM doubles per column, issued by BN threads) ----
+            mbar_wait(v_free, free_phase);
+            free_phase ^= 1u;
+            if (staged) {
+                if (tid < BN) {
+                    mbar_expect_tx(v_full, (unsigned)(BM * sizeof(double)));
+                    bulk_g2s(VT + (size_t)tid * BMP, gather_base(sch) + (size_t)staged_id * p.LD, BM * sizeof(double), v_full);
                 }
+                mbar_wait(v_full, vfull_phase);
+                vfull_phase ^= 1u;
             }
+            // the product, in place: a thread reads and writes only its own elements.  States >= S do not exist: zero rows (the matrix
+            // rows there may be real).
+#pragma unroll
+            for (int j = 0; j < TNW; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double* const vt = VT + (size_t)(col_base + j * 8 + e) * BMP + row_base;
+#pragma unroll
+                    for (int i = 0; i < TMW; ++i) {
+                        const bool live = sp.is_root || row_base + i * 8 < p.S;
+                        double v = has_acc ? acc[i][j][e] : 1.0;
+                        if (staged) {
+                            const double f = vt[i * 8];
+                            v = has_acc ? __dmul_rn(v, f) : f;
+                        }
+                        vt[i * 8] = live ? v : 0.0;
+                    }
+                }
             __syncthreads();
 
             // The next step's leaf counts come from DRAM (the count table is streamed once per category): pull their lines into L2 now, a
@@ -263,6 +305,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                 for (int i = 0; i < TMW; ++i)
 #pragma unroll
                     for (int j = 0; j < TNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+                const double* const Bw = VT + (size_t)(wn * 8 * TNW + g) * BMP + q;     // + j*8*BMP + state
                 for (int chunk = 0; chunk < n_chunks; ++chunk) {
                     if (PRODUCE_FIRST) produce_one();               // refill the stage the previous chunk released: NS-1 chunks of lead
                     long long t_a = 0, t_b = 0, t_c = 0;
@@ -270,16 +313,15 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     mbar_wait(full_bar + c_stage, c_phase);
                     if (PROBE) t_b = clock64();
                     const double* As = stages + (size_t)c_stage * Cfg::STAGE_DOUBLES;
-                    const double* Bs = Vres + (size_t)chunk * BK * BNP;
+                    const double* Bs = Bw + chunk * BK;
 #pragma unroll
                     for (int k4 = 0; k4 < BK / 4; ++k4) {
                         double a[TMW], b[TNW];
                         const double* ap = As + (k4 * 4 + q) * BMP + row_base;
-                        const double* bp = Bs + (k4 * 4 + q) * BNP;
 #pragma unroll
                         for (int i = 0; i < TMW; ++i) a[i] = ap[i * 8];
 #pragma unroll
-                        for (int j = 0; j < TNW; ++j) b[j] = bp[(wn * 8 * TNW + j * 8 + g) ^ swz_q];
+                        for (int j = 0; j < TNW; ++j) b[j] = Bs[(size_t)j * 8 * BMP + k4 * 4];
 #pragma unroll
                         for (int i = 0; i < TMW; ++i) {
                             // A warp's DMMAs issue exactly 16 cycles apart (ptxas: stall 15 + NOP) and it cannot catch up on time spent elsewhere,
@@ -304,7 +346,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                         ++probe_n;
                     }
                 }
-                // ---- 4. the factor stays in registers for the parent, or is parked once in a global slot ----
+                // ---- 4. the factor stays in registers for the parent, is parked once in a global slot, or becomes table rows ----
                 if (JOBS && sp.dst_kind == 3) {
                     // one table row per pattern: the transposed layout the gathers of the parent read
                     double* __restrict__ tb = p.tables + ((size_t)sp.f_slot * p.K + (size_t)k * U) * p.LD;
@@ -329,10 +371,10 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                 }
             } else {
                 // ---- root epilogue from shared memory: index j <-> root size j+1 (core.cpp:141), weighted by prior(j)
-                root_epilogue<BN, Cfg::PARTS, true>(p, Vres, BNP, red, tid, k, col0);
+                root_epilogue<BN, Cfg::PARTS, true>(p, VT, BMP, red, tid, k, col0);
             }
         }
-        __syncthreads();   // factor slots of this tile are dead; Vres / red are reused by the next tile
+        __syncthreads();   // factor slots of this tile are dead; VT / red are reused by the next tile
     }
 }
 
