@@ -240,6 +240,9 @@ void plan_tables(cafe_b200_ctx* c, std::vector<int32_t>& counts_t, int n_leaves)
     counts_t.resize((size_t)(n_leaves + extra) * US, 0);
     for (const TableNode& t : c->tnodes)
         if (pseudo[t.node]) std::copy(ids[t.node].begin(), ids[t.node].end(), counts_t.begin() + (size_t)c->leaf_row_of_node[t.node] * US);
+    c->tab_ids_host.assign(c->tnodes.size() * (size_t)US, 0);        // the Pupko traceback needs every table node's pattern id per family
+    for (size_t i = 0; i < c->tnodes.size(); ++i)
+        std::copy(ids[c->tnodes[i].node].begin(), ids[c->tnodes[i].node].end(), c->tab_ids_host.begin() + i * (size_t)US);
     build_schedule(c, pseudo, c->tsched_main);
     // table launches: level by level, at most MAX_TABLE_JOBS nodes per launch; job j = step j (one step, all children gathers)
     c->tsched_jobs.clear();
@@ -616,6 +619,124 @@ PruneParams base_params(cafe_b200_ctx* c, int K, int mode)
     return p;
 }
 
+// ---- Pupko, second design (pupko2.cuh): table launches level by level, the main pass, the traceback; matrices are already there ----
+void reconstruct_v2(cafe_b200_ctx* c, int K)
+{
+    const int n = c->n_nodes;
+    const bool tabs = c->tables_on;
+    const Schedule* main_sched = tabs ? &c->tsched_main : nullptr;
+    if (!c->p2_ready) {
+        const std::vector<Step>& st = tabs ? main_sched->steps : c->steps;
+        const std::vector<StepChild>& ch = tabs ? main_sched->children : c->children;
+        c->d_p2_steps.reserve(st.size());
+        CK(cudaMemcpy(c->d_p2_steps.p, st.data(), st.size() * sizeof(Step), cudaMemcpyHostToDevice));
+        c->d_p2_children.reserve(std::max<size_t>(ch.size(), 1));
+        CK(cudaMemcpy(c->d_p2_children.p, ch.data(), ch.size() * sizeof(StepChild), cudaMemcpyHostToDevice));
+        c->d_p2_parent.reserve(n); c->d_p2_leaf_col.reserve(n); c->d_p2_tab_of.reserve(n);
+        CK(cudaMemcpy(c->d_p2_parent.p, c->parent.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_p2_leaf_col.p, c->leaf_col.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        std::vector<int32_t> tab_of(n, -1);
+        if (tabs) for (int v = 0; v < n; ++v) tab_of[v] = c->tnode_of[v];
+        CK(cudaMemcpy(c->d_p2_tab_of.p, tab_of.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->d_p2_tab_ids.reserve(std::max<size_t>(c->tab_ids_host.size(), 1));
+        if (tabs && !c->tab_ids_host.empty())
+            CK(cudaMemcpy(c->d_p2_tab_ids.p, c->tab_ids_host.data(), c->tab_ids_host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (tabs) {
+            c->d_p2_job_steps.resize(c->tsched_jobs.size());
+            c->d_p2_job_children.resize(c->tsched_jobs.size());
+            for (size_t g = 0; g < c->tsched_jobs.size(); ++g) {
+                const Schedule& sc = c->tsched_jobs[g];
+                c->d_p2_job_steps[g].reserve(sc.steps.size());
+                CK(cudaMemcpy(c->d_p2_job_steps[g].p, sc.steps.data(), sc.steps.size() * sizeof(Step), cudaMemcpyHostToDevice));
+                c->d_p2_job_children[g].reserve(sc.children.size());
+                CK(cudaMemcpy(c->d_p2_job_children[g].p, sc.children.data(), sc.children.size() * sizeof(StepChild), cudaMemcpyHostToDevice));
+            }
+        }
+        c->p2_ready = true;
+    }
+    // geometry: 512 threads need at least 32 columns; the tile must fit shared memory
+    while (c->TN > 1 && pupko2_smem_bytes(c->TM, c->TN) > c->smem_optin) c->TN >>= 1;
+    if (pupko2_smem_bytes(c->TM, c->TN) > c->smem_optin) throw CudaError{"RANGE: state space too large for the shared memory of the Pupko kernel"};
+    const int bn = 16 * c->TN, bm = 16 * c->TM;
+    c->n_col_tiles = (int)((c->U + bn - 1) / bn);
+    c->grid = (int)std::min<int64_t>((int64_t)c->n_col_tiles * K, c->n_sms);
+    const int SP = (c->S + 7) / 8 * 8;
+    // argmax tables: one per internal non-root node, over its own columns
+    std::vector<int64_t> coff(2 * (size_t)n, 0);
+    int64_t total = 0;
+    for (int v = 0; v < n - 1; ++v) {
+        if (c->leaf_col[v] >= 0) continue;
+        const int64_t cols = tabs && c->tnode_of[v] >= 0 ? c->tnodes[c->tnode_of[v]].D : c->U;
+        coff[v] = total;
+        coff[n + v] = cols;
+        total += cols * SP * K;
+    }
+    c->d_p2_coff.reserve(coff.size());
+    CK(cudaMemcpyAsync(c->d_p2_coff.p, coff.data(), coff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));            // coff is a stack vector
+    c->d_p2_ctab.reserve((size_t)std::max<int64_t>(total, 1));
+    c->d_p2_root.reserve((size_t)K * c->U_stride);
+    const int n_fslots = tabs ? main_sched->n_fslots : c->n_fslots;
+    Pupko2Params p{};
+    p.mat_of = c->d_mat_of.p;
+    p.arena = c->d_arena.p;
+    p.prior_d = c->d_prior.p;
+    p.slot_stride = (int64_t)bm * bn;
+    c->d_scratch.reserve((size_t)c->grid * n_fslots * p.slot_stride);
+    p.scratch = c->d_scratch.p;
+    if (tabs) c->d_tables.reserve((size_t)c->table_rows * K * c->LD, true);
+    p.tables = c->d_tables.p;
+    p.ctab = c->d_p2_ctab.p;
+    p.c_off = c->d_p2_coff.p;
+    p.c_cols = c->d_p2_coff.p + n;
+    p.root_state = c->d_p2_root.p;
+    p.U = c->U; p.U_stride = c->U_stride;
+    p.n_nodes = n; p.n_fslots = n_fslots;
+    p.LD = c->LD; p.S = c->S; p.SP = SP; p.R = c->R; p.N = c->N; p.K = K;
+    p.root_len = std::min(c->max_family_size, c->R) + 1;
+    p.n_col_tiles = c->n_col_tiles;
+    if (tabs) {
+        std::vector<int32_t> jobs;
+        std::vector<size_t> job_off;
+        std::vector<int> job_tiles;
+        for (size_t g = 0; g < c->tjobs.size(); ++g) {
+            job_off.push_back(jobs.size());
+            int tile = 0;
+            for (int ti : c->tjobs[g]) {
+                const TableNode& t = c->tnodes[ti];
+                const int ncol = (int)((t.D + bn - 1) / bn);
+                const int32_t w[JOB_WORDS] = {tile, ncol, (int32_t)t.D, (int32_t)t.D_stride, (int32_t)(uint32_t)(t.ids_off & 0xffffffff),
+                                              (int32_t)(t.ids_off >> 32), 0, 0};
+                jobs.insert(jobs.end(), w, w + JOB_WORDS);
+                tile += ncol * K;
+            }
+            job_tiles.push_back(tile);
+        }
+        c->d_p2_jobs.reserve(std::max<size_t>(jobs.size(), 1));
+        CK(cudaMemcpyAsync(c->d_p2_jobs.p, jobs.data(), jobs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t g = 0; g < c->tjobs.size(); ++g) {
+            Pupko2Params pj = p;
+            pj.steps = c->d_p2_job_steps[g].p;
+            pj.children = c->d_p2_job_children[g].p;
+            pj.jobs = c->d_p2_jobs.p + job_off[g];
+            pj.n_jobs = (int)c->tjobs[g].size();
+            pj.n_job_tiles = job_tiles[g];
+            pj.ids = c->d_ids.p;
+            pj.n_steps = pj.n_jobs;
+            CK(launch_pupko2(c->TM, c->TN, std::min(job_tiles[g], c->n_sms), c->stream, pj, true));
+        }
+    }
+    p.steps = c->d_p2_steps.p;
+    p.children = c->d_p2_children.p;
+    p.ids = c->d_counts_t.p;
+    p.n_steps = (int)(tabs ? main_sched->steps.size() : c->steps.size());
+    CK(launch_pupko2(c->TM, c->TN, c->grid, c->stream, p, false));
+    c->d_states.reserve((size_t)K * c->U_stride * n);
+    CK(launch_pupko_traceback(c->stream, c->d_p2_ctab.p, c->d_p2_coff.p, c->d_p2_coff.p + n, c->d_p2_parent.p, c->d_p2_leaf_col.p,
+                              c->d_p2_tab_of.p, c->d_p2_tab_ids.p, c->d_p2_root.p, c->U, c->U_stride, n, K, SP, c->d_states.p));
+}
+
 bool lambdas_valid(const double* lambdas, int n)
 {
     // single_lambda::is_valid: lambda > 0 (lambda.h:58-60); multiple_lambda::is_valid: none < 0 (lambda.cpp:59-62)
@@ -773,6 +894,7 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         if (const char* e = std::getenv("CAFE_B200_RESIDENT_WN")) { int v = std::atoi(e); c->resident_wn = v == 4 ? 4 : 2; }
         if (const char* e = std::getenv("CAFE_B200_RESIDENT_PROBE")) c->resident_probe = std::atoi(e) != 0;
         if (const char* e = std::getenv("CAFE_B200_PUPKO_THREADS")) c->pupko_threads = std::atoi(e) == 256 ? 256 : 512;
+        if (const char* e = std::getenv("CAFE_B200_PUPKO")) c->pupko_version = std::atoi(e) == 1 ? 1 : 2;
         if (const char* e = std::getenv("CAFE_B200_MATGEN")) { c->matgen_entry = std::strcmp(e, "entry") == 0; c->matgen_libexp = std::strcmp(e, "rows") == 0; }
         if (const char* e = std::getenv("CAFE_B200_PRUNE")) {
             const std::string v(e);
@@ -895,6 +1017,10 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     c->d_significant.release(); c->d_failed.release(); c->d_pupko_m.release(); c->d_states.release();
     c->d_leaf_row.release(); c->d_states_f.release(); c->d_cat_states_f.release(); c->d_avg_f.release();
     c->d_ids.release(); c->d_tables.release();
+    c->d_p2_steps.release(); c->d_p2_children.release(); c->d_p2_jobs.release(); c->d_p2_tab_of.release(); c->d_p2_tab_ids.release();
+    c->d_p2_parent.release(); c->d_p2_leaf_col.release(); c->d_p2_root.release(); c->d_p2_coff.release(); c->d_p2_ctab.release();
+    for (auto& b : c->d_p2_job_steps) b.release();
+    for (auto& b : c->d_p2_job_children) b.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1253,6 +1379,8 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         launch_matrices(c, (int)kp.params.size());
 
         choose_columns(c, K);
+        if (c->pupko_version == 2 && c->n_mtiles == 1) reconstruct_v2(c, K);
+        else {
         // the column tile must also fit shared memory (M_v tile + stages + traceback states of every step): narrow it until it does
         while (c->TN > 1 && pupko_smem_bytes(c->TM, c->TN, c->S, (int)c->steps.size()) > c->smem_optin) {
             c->TN >>= 1;
@@ -1284,13 +1412,19 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
         p.root_len = std::min(c->max_family_size, c->R) + 1;
         p.n_col_tiles = c->n_col_tiles; p.n_mtiles = c->n_mtiles;
         CK(launch_pupko(c->TM, c->TN, c->grid, c->S, c->stream, p, c->pupko_threads));
+        }
         const int n = c->n_nodes;
         const size_t Fn = (size_t)c->F * n;
         c->d_cat_probs.reserve(K);
         static const double one_prob = 1.0;
         CK(cudaMemcpyAsync(c->d_cat_probs.p, n_cat > 0 ? cat_probs : &one_prob, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         c->d_leaf_row.reserve(n);
-        CK(cudaMemcpyAsync(c->d_leaf_row.p, c->leaf_row_of_node.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        // rows of the count table for the LEAVES only: leaf_row_of_node also names the pattern-id rows of the table nodes the main
+        // pruning pass gathers (internal nodes), which must keep their reconstructed state
+        std::vector<int32_t> true_leaf_row(n);
+        for (int i = 0; i < n; ++i) true_leaf_row[i] = c->leaf_col[i] >= 0 ? c->leaf_row_of_node[i] : -1;
+        CK(cudaMemcpyAsync(c->d_leaf_row.p, true_leaf_row.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));            // true_leaf_row is a stack vector
         c->d_states_f.reserve(Fn);
         if (cat_states) c->d_cat_states_f.reserve(Fn * K);
         if (averaged) c->d_avg_f.reserve(Fn);

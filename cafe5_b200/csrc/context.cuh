@@ -199,6 +199,17 @@ struct cafe_b200_ctx {
     std::vector<std::vector<int>> tjobs;   // table nodes (indices into tnodes) of every table launch
     cafe::DevBuf<int32_t> d_ids;
     cafe::DevBuf<double> d_tables;
+    // Pupko, second design (pupko2.cuh): built on first use
+    std::vector<int32_t> tab_ids_host;     // [tnodes.size()][U_stride] pattern id of every unique family at every table node
+    bool p2_ready = false;
+    cafe::DevBuf<cafe::Step> d_p2_steps;             // main schedule (reduced when tables are on)
+    cafe::DevBuf<cafe::StepChild> d_p2_children;
+    std::vector<cafe::DevBuf<cafe::Step>> d_p2_job_steps;        // per table launch
+    std::vector<cafe::DevBuf<cafe::StepChild>> d_p2_job_children;
+    cafe::DevBuf<int32_t> d_p2_jobs, d_p2_tab_of, d_p2_tab_ids, d_p2_parent, d_p2_leaf_col, d_p2_root;
+    cafe::DevBuf<int64_t> d_p2_coff;                 // [2][n_nodes]: offsets, columns
+    cafe::DevBuf<uint16_t> d_p2_ctab;
+    int pupko_version = 2;                           // CAFE_B200_PUPKO=1: the round-1 kernel (pupko.cuh)
     cafe::KeyPlan last_kp;                 // key plan of the evaluation being launched
     int last_table_launches = 0;
     int64_t last_columns = 0;              // contraction columns x categories executed by the last evaluation (tables + main pass)

@@ -4,6 +4,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "pupko.cuh"
+#include "pupko2.cuh"
 
 namespace cafe {
 
@@ -34,5 +35,11 @@ cudaError_t launch_prune_resident_wn2_tables(int TM, int TNW, int grid, int N, i
 cudaError_t launch_prune_resident_wn2probe(int TM, int TNW, int grid, int N, int n_stages, cudaStream_t stream, const PruneParams& p, const InlineSchedule& sched);
 // Pupko reconstruction (pupko.cuh).  threads = 512 (default geometry when TN >= 2) or 256.
 cudaError_t launch_pupko(int TM, int TN, int grid, int S, cudaStream_t stream, const PupkoParams& p, int threads);
+
+// Pupko, second design (pupko2.cuh): argmax tables + chained values + subtree-pattern tables; jobs = a table launch
+cudaError_t launch_pupko2(int TM, int TN, int grid, cudaStream_t stream, const Pupko2Params& p, bool jobs);
+cudaError_t launch_pupko_traceback(cudaStream_t stream, const void* ctab, const int64_t* c_off, const int64_t* c_cols, const int32_t* parent,
+                                   const int32_t* leaf_col, const int32_t* tab_of, const int32_t* tab_ids, const int32_t* root_state,
+                                   int64_t U, int64_t U_stride, int n_nodes, int K, int SP, int32_t* states);
 
 }  // namespace cafe
