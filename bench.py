@@ -173,16 +173,16 @@ def make_workload(args, device):
     return tree, counts, mfs, mrs, {"simulate_s": t_sim, "simulated": int(n_draw), "not_at_root": int(sim["n_not_at_root"])}
 
 
-def drop_failing_families(args, tree, counts, mfs, mrs, lo, hi, device):
+def drop_failing_families(args, tree, counts, mfs, mrs, members, device):
     """The reference rejects a whole evaluation (+inf) when ONE family's root vector underflows to zero in some category
     (gamma_core.cpp:151,216-225); among a million simulated families on 118 branches a few dozen do, near the generating
     parameters.  A user has to remove such families before the reference returns a finite score; the bench does the same: a
-    family of this rank's shard [lo, hi) that fails anywhere in the parameter box the steps walk through is replaced by a copy
-    of a healthy one (so the family count is unchanged; duplicates are not counted in the throughput numerator)."""
+    family of this rank's shard (`members`: its family indices) that fails anywhere in the parameter box the steps walk through is
+    replaced by a copy of a healthy one (so the family count is unchanged; duplicates are not counted in the throughput numerator)."""
     from cafe5_b200 import families as fam
     from cafe5_b200.gamma import get_gamma
     from cafe5_b200.model import Context
-    shard = counts[lo:hi].copy()
+    shard = counts[members].copy()
     ctx = Context(tree, shard, mfs, mrs, device=device)
     ctx.set_prior(fam.uniform_prior(mrs))
     bad = np.zeros(shard.shape[0], dtype=bool)
@@ -347,8 +347,8 @@ def workload_config(args, tree):
                         "(matrices + pruning + mixture + score)" % (args.cats, args.families, args.taxa, tree.n_nodes),
             "families": args.families, "categories": args.cats, "taxa": args.taxa,
             "l2": "flushed between timed steps (256 MiB write on the same stream, outside the event pair)",
-            "parallelism": "families sharded contiguously over the GPUs (strong scaling: the job does not grow with --gpus); "
-                           "one 16-byte-per-rank all_gather per step, inside the timed region"}
+            "parallelism": "the job's families sharded over the GPUs (strong scaling: the job does not grow with --gpus) in clustered, "
+                           "work-balanced shards (cafe_b200_plan_shards); one 16-byte-per-rank all_gather per step, inside the timed region"}
 
 
 class DeviceResult:
@@ -388,8 +388,18 @@ def run_ours(args):
 
     t_setup0 = time.perf_counter()
     tree, all_counts, mfs, mrs, gen_info = make_workload(args, local)
-    lo, hi = cdist.shard_bounds(args.families, world, rank)
-    counts, n_replaced = drop_failing_families(args, tree, all_counts, mfs, mrs, lo, hi, local)
+    # strong scaling: the job is cut into clustered, work-balanced shards (cafe_b200_plan_shards: families ordered by total count,
+    # cut points moved until every shard costs the same under the subtree-pattern table plan); every rank computes the same plan
+    t0 = time.perf_counter()
+    if world > 1:
+        from cafe5_b200.model import plan_shards
+        order, bounds = plan_shards(tree, all_counts, world)
+    else:
+        order, bounds = np.arange(args.families), np.array([0, args.families])
+    gen_info["plan_shards_s"] = time.perf_counter() - t0
+    gen_info["shard_sizes"] = np.diff(bounds).tolist()
+    members = order[bounds[rank]:bounds[rank + 1]]
+    counts, n_replaced = drop_failing_families(args, tree, all_counts, mfs, mrs, members, local)
     prior = fam.uniform_prior(mrs)
     t0 = time.perf_counter()
     ctx = Context(tree, counts, mfs, mrs, device=local)
@@ -504,8 +514,7 @@ def run_ours(args):
         if rank == 0:
             # every rank holds the same simulated table; the failing families were replaced shard by shard, so rebuild the job's
             # table from the shards' healthy view: rank 0 repeats the (deterministic) replacement for every shard
-            parts = [drop_failing_families(args, tree, all_counts, mfs, mrs, *cdist.shard_bounds(args.families, world, r), local)[0]
-                     for r in range(world)]
+            parts = [drop_failing_families(args, tree, all_counts, mfs, mrs, order[bounds[r]:bounds[r + 1]], local)[0] for r in range(world)]
             job = np.concatenate(parts)
             mctx = Context(tree, job, mfs, mrs, devices=list(range(world)))
             mctx.set_prior(prior)

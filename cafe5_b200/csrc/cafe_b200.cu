@@ -790,7 +790,8 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
     if (!gamma) {
         finish_base_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_best.p, c->d_f2u.p, c->F, c->d_family_lnl.p, c->d_partial.p);
         CK(cudaGetLastError());
-        final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, nullptr, nb, c->d_result.p);
+        if (c->F <= SEQ_SUM_LIMIT) final_sum_sequential_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_family_lnl.p, c->F, nullptr, 0, c->d_result.p);
+        else final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, nullptr, nb, c->d_result.p);
     } else {
         c->d_cat_lk.reserve((size_t)c->F * K);
         c->d_posterior.reserve((size_t)c->F * K);
@@ -801,9 +802,11 @@ bool enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambda, double 
         CK(cudaMemcpyAsync(c->d_cat_probs.p, cat_probs, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         finish_gamma_kernel<<<nb, FIN_THREADS, 0, c->stream>>>(c->d_best.p, c->d_ok.p, c->U_stride, c->d_f2u.p, c->F, K,
                                                                c->d_cat_probs.p, c->d_cat_lk.p, c->d_family_lk.p, c->d_posterior.p,
-                                                               c->d_significant.p, c->d_failed.p, c->d_partial.p, c->d_partial_fail.p);
+                                                               c->d_significant.p, c->d_failed.p, c->d_family_lnl.p, c->d_partial.p, c->d_partial_fail.p);
         CK(cudaGetLastError());
-        final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, c->d_partial_fail.p, nb, c->d_result.p);
+        if (c->F <= SEQ_SUM_LIMIT)
+            final_sum_sequential_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_family_lnl.p, c->F, c->d_partial_fail.p, nb, c->d_result.p);
+        else final_sum_kernel<<<1, FIN_THREADS, 0, c->stream>>>(c->d_partial.p, c->d_partial_fail.p, nb, c->d_result.p);
     }
     CK(cudaGetLastError());
     c->last_launches = (c->matgen_entry ? 4 : 5) + c->last_table_launches;   // [pow table +] matrices, [factor tables,] pruning, finish, final sum
@@ -1003,6 +1006,7 @@ int cafe_b200_destroy(cafe_b200_ctx* c)
     if (!c) return CAFE_B200_OK;
     if (c->is_group()) {
         delete c->pool;
+        if (c->g_scratch) cudaFreeHost(c->g_scratch);
         for (cafe_b200_ctx* s : c->shards) if (s) cafe_b200_destroy(s);
         delete c;
         return CAFE_B200_OK;
@@ -1445,6 +1449,129 @@ int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int32_t n_lam
 }  // extern "C"
 
 // ================================================================================================
+// Clustered, work-balanced shards (strong scaling).  Every shard plans its own subtree-pattern tables, and a random
+// block of the job shares fewer patterns than the whole job does (tools/probes/shard_clustering_study.py: 45 % of the columns left at 8
+// random shards against 35 % for the whole job).  Families with similar counts share the most patterns, so the job is ordered by
+// total count and cut into contiguous blocks of that order; blocks of large families keep more distinct patterns per family, so the
+// cut points are moved until every block costs the same number of contraction columns under the table plan.
+namespace {
+
+// contraction columns per category the table plan leaves for the families idx[0 .. n): sum over the non-root internal nodes of
+// (patterns of a table node | distinct families otherwise) -- the rule of plan_tables, evaluated on the host without a context
+int64_t plan_cost(const cafe_b200_tree* tree, const int32_t* counts, int n_species, const int64_t* idx, int64_t n)
+{
+    const int nn = tree->n_nodes;
+    const char* mode = std::getenv("CAFE_B200_TABLES");
+    const bool off = mode && std::strcmp(mode, "0") == 0, force = mode && std::strcmp(mode, "force") == 0;
+    double frac = force ? 1.0 : 0.75;
+    if (const char* e = std::getenv("CAFE_B200_TABLE_FRAC")) frac = std::atof(e);
+    std::vector<int> leaves;
+    int n_internal = 0;
+    for (int v = 0; v < nn; ++v) { if (tree->leaf_col[v] >= 0) leaves.push_back(v); else if (v != nn - 1) ++n_internal; }
+    // distinct families
+    std::unordered_map<std::string, int32_t> seen;
+    seen.reserve((size_t)n * 2);
+    std::vector<int64_t> uniq;
+    std::string key(leaves.size() * sizeof(int32_t), '\0');
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t* row = counts + (size_t)idx[i] * n_species;
+        for (size_t j = 0; j < leaves.size(); ++j) memcpy(&key[j * sizeof(int32_t)], &row[tree->leaf_col[leaves[j]]], sizeof(int32_t));
+        if (seen.emplace(key, (int32_t)uniq.size()).second) uniq.push_back(idx[i]);
+    }
+    const int64_t U = (int64_t)uniq.size();
+    if (off || (!force && U < 8192)) return U * n_internal;
+    std::vector<std::vector<int>> kids(nn);
+    for (int i = nn - 1; i >= 0; --i) if (tree->parent[i] >= 0) kids[tree->parent[i]].push_back(i);
+    std::vector<std::vector<int32_t>> ids(nn);
+    std::vector<char> is_table(nn, 0);
+    auto id_of = [&](int v, int64_t u) -> int32_t {
+        return tree->leaf_col[v] >= 0 ? counts[(size_t)uniq[u] * n_species + tree->leaf_col[v]] : ids[v][u];
+    };
+    int64_t cost = 0;
+    const int64_t limit = (int64_t)std::floor(frac * (double)U);
+    for (int v = 0; v < nn - 1; ++v) {
+        if (tree->leaf_col[v] >= 0) continue;
+        bool ok = true;
+        for (int k : kids[v]) if (tree->leaf_col[k] < 0 && !is_table[k]) { ok = false; break; }
+        int64_t D = 0;
+        bool over = !ok;
+        if (ok) {
+            std::vector<int32_t> id(U);
+            const int m = (int)kids[v].size();
+            if (m == 2) {
+                std::unordered_map<uint64_t, int32_t> pat;
+                for (int64_t u = 0; u < U; ++u) {
+                    const uint64_t kk = ((uint64_t)(uint32_t)id_of(kids[v][0], u) << 32) | (uint32_t)id_of(kids[v][1], u);
+                    auto it = pat.find(kk);
+                    if (it == pat.end()) {
+                        if (D >= limit) { over = true; break; }
+                        it = pat.emplace(kk, (int32_t)D++).first;
+                    }
+                    id[u] = it->second;
+                }
+            } else {
+                std::unordered_map<std::string, int32_t> pat;
+                std::string pk((size_t)m * sizeof(int32_t), '\0');
+                for (int64_t u = 0; u < U; ++u) {
+                    for (int j = 0; j < m; ++j) { const int32_t x = id_of(kids[v][j], u); memcpy(&pk[(size_t)j * sizeof x], &x, sizeof x); }
+                    auto it = pat.find(pk);
+                    if (it == pat.end()) {
+                        if (D >= limit) { over = true; break; }
+                        it = pat.emplace(pk, (int32_t)D++).first;
+                    }
+                    id[u] = it->second;
+                }
+            }
+            if (!over && D > 0) { is_table[v] = 1; ids[v] = std::move(id); }
+        }
+        cost += is_table[v] ? D : U;
+        for (int k : kids[v]) if (tree->leaf_col[k] < 0) std::vector<int32_t>().swap(ids[k]);     // children's ids are no longer needed
+    }
+    return cost;
+}
+
+}  // namespace
+
+extern "C" int cafe_b200_plan_shards(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
+                                     int32_t n_shards, int64_t* order, int64_t* bounds)
+{
+    if (!tree || !counts || n_families <= 0 || n_species <= 0 || n_shards < 1 || !order || !bounds) return CAFE_B200_ERR_ARG;
+    n_shards = (int32_t)std::min<int64_t>(n_shards, n_families);
+    std::vector<int64_t> total((size_t)n_families, 0);
+    for (int64_t f = 0; f < n_families; ++f)
+        for (int j = 0; j < n_species; ++j) total[f] += counts[(size_t)f * n_species + j];
+    for (int64_t f = 0; f < n_families; ++f) order[f] = f;
+    std::stable_sort(order, order + n_families, [&](int64_t a, int64_t b) { return total[a] < total[b]; });
+    std::vector<double> size((size_t)n_shards, (double)n_families / n_shards);
+    auto set_bounds = [&]() {
+        double acc = 0;
+        bounds[0] = 0;
+        for (int i = 0; i < n_shards; ++i) {
+            acc += size[i];
+            bounds[i + 1] = i + 1 == n_shards ? n_families : std::max<int64_t>(bounds[i] + 1, std::min<int64_t>((int64_t)std::llround(acc), n_families - (n_shards - 1 - i)));
+        }
+    };
+    set_bounds();
+    if (n_shards == 1) return CAFE_B200_OK;
+    for (int iter = 0; iter < 3; ++iter) {
+        std::vector<int64_t> cost((size_t)n_shards, 0);
+        std::vector<std::thread> workers;
+        for (int i = 0; i < n_shards; ++i)
+            workers.emplace_back([&, i] { cost[i] = plan_cost(tree, counts, n_species, order + bounds[i], bounds[i + 1] - bounds[i]); });
+        for (auto& w : workers) w.join();
+        // a block's cost per family is taken as constant while its size changes a little: sizes proportional to 1 / (cost per family)
+        double norm = 0;
+        std::vector<double> inv((size_t)n_shards);
+        for (int i = 0; i < n_shards; ++i) { inv[i] = (double)(bounds[i + 1] - bounds[i]) / std::max<double>((double)cost[i], 1.0); norm += inv[i]; }
+        const int64_t cmax = *std::max_element(cost.begin(), cost.end()), cmin = *std::min_element(cost.begin(), cost.end());
+        if ((double)(cmax - cmin) <= 0.01 * (double)cmax) break;          // within 1 %: balanced
+        for (int i = 0; i < n_shards; ++i) size[i] = 0.5 * size[i] + 0.5 * (double)n_families * inv[i] / norm;   // damped
+        set_bounds();
+    }
+    return CAFE_B200_OK;
+}
+
+// ================================================================================================
 // cafe_b200_create_multi: families sharded contiguously over the devices of one node.  Every group call runs the
 // single-device entry point of all shards at once on the shard workers; per-family outputs land in the caller's buffers at the
 // shard's offset; the scalar partials are added on the host in shard order.
@@ -1461,12 +1588,28 @@ extern "C" int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t*
     g->shards.assign(n_shards, nullptr);
     g->shard_begin.resize(n_shards + 1);
     for (int i = 0; i <= n_shards; ++i) g->shard_begin[i] = n_families * i / n_shards;
+    // Large jobs: clustered, work-balanced shards (cafe_b200_plan_shards) instead of blocks in the caller's order, so that the
+    // per-shard subtree-pattern tables keep most of the whole job's reuse.  CAFE_B200_CLUSTER=0 keeps the caller's order.
+    std::vector<int32_t> packed;
+    const char* cl = std::getenv("CAFE_B200_CLUSTER");
+    if (n_families >= (int64_t)8192 * n_shards && !(cl && std::strcmp(cl, "0") == 0)) {
+        g->order.resize((size_t)n_families);
+        if (cafe_b200_plan_shards(tree, counts, n_families, n_species, n_shards, g->order.data(), g->shard_begin.data()) != CAFE_B200_OK) {
+            delete g;
+            create_error() = "shard planning failed";
+            return CAFE_B200_ERR_ARG;
+        }
+        packed.resize((size_t)n_families * n_species);
+        for (int64_t p = 0; p < n_families; ++p)
+            memcpy(&packed[(size_t)p * n_species], counts + (size_t)g->order[p] * n_species, n_species * sizeof(int32_t));
+    }
+    const int32_t* src = packed.empty() ? counts : packed.data();
     g->pool = new ShardPool(n_shards);
     std::vector<std::string> errs(n_shards);
     int bad = -1;
     const int rc = g->pool->run([&](int i) {
         const int64_t b = g->shard_begin[i], e = g->shard_begin[i + 1];
-        const int r = cafe_b200_create(tree, counts + (size_t)b * n_species, e - b, n_species, max_family_size, max_root_family_size,
+        const int r = cafe_b200_create(tree, src + (size_t)b * n_species, e - b, n_species, max_family_size, max_root_family_size,
                                        devices[i], &g->shards[i]);
         if (r != CAFE_B200_OK) errs[i] = cafe_b200_last_error(nullptr);   // create's error text is per thread
         return r;
@@ -1486,7 +1629,12 @@ extern "C" int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t*
     g->S = s0->S; g->R = s0->R; g->N = s0->N;
     g->branch_length = s0->branch_length;
     g->parent = s0->parent; g->leaf_col = s0->leaf_col; g->lambda_class = s0->lambda_class;
-    for (const cafe_b200_ctx* sh : g->shards) g->max_count.insert(g->max_count.end(), sh->max_count.begin(), sh->max_count.end());
+    g->max_count.resize((size_t)n_families);
+    for (int i = 0; i < n_shards; ++i)
+        for (int64_t j = 0; j < g->shards[i]->F; ++j) {
+            const int64_t pos = g->shard_begin[i] + j;
+            g->max_count[(size_t)(g->order.empty() ? pos : g->order[pos])] = g->shards[i]->max_count[j];
+        }
     *out = g;
     return CAFE_B200_OK;
 }
@@ -1588,25 +1736,42 @@ double combine(const std::vector<double>& neg)
     return total;
 }
 
-// A per-family output of the caller (width values per family).  Contiguous shards write straight into it at their offset; bucket
-// shards (g->order non-empty) write bucket-major into a scratch copy that finish() scatters back to the caller's family order.
+// A per-family output of the caller (width values per family).  Contiguous shards write straight into it at their offset; shards that
+// are not contiguous in the caller's order (buckets, clustered shards: g->order non-empty) write shard-major into page-locked scratch
+// of the group and every shard worker scatters its own rows back to the caller's family order.
 template <typename T>
 struct Out {
     cafe_b200_ctx* g;
     T* user;
     size_t width;
-    std::vector<T> tmp;
+    T* tmp = nullptr;
     Out(cafe_b200_ctx* g_, T* user_, size_t width_) : g(g_), user(user_), width(width_)
     {
-        if (user && !g->order.empty()) tmp.resize((size_t)g->F * width);
+        if (user && !g->order.empty()) {
+            tmp = (T*)g->take_scratch((size_t)g->F * width * sizeof(T));
+            if (!tmp) throw CudaError{"group scratch exhausted"};
+        }
     }
-    T* at(int shard) { return !user ? nullptr : (tmp.empty() ? user : tmp.data()) + (size_t)g->shard_begin[shard] * width; }
-    void finish()
+    T* at(int shard) { return !user ? nullptr : (tmp ? tmp : user) + (size_t)g->shard_begin[shard] * width; }
+    void scatter(int shard)
     {
-        if (!user || tmp.empty()) return;
-        for (int64_t p = 0; p < g->F; ++p) memcpy(user + (size_t)g->order[p] * width, tmp.data() + (size_t)p * width, width * sizeof(T));
+        if (!tmp) return;
+        for (int64_t p = g->shard_begin[shard]; p < g->shard_begin[shard + 1]; ++p)
+            memcpy(user + (size_t)g->order[p] * width, tmp + (size_t)p * width, width * sizeof(T));
     }
 };
+
+// makes sure the group's scratch holds `bytes` (page-locked; contents live for one call) and resets it
+void reset_scratch(cafe_b200_ctx* g, size_t bytes)
+{
+    g->g_scratch_used = 0;
+    if (g->order.empty() || bytes <= g->g_scratch_cap) return;
+    if (g->g_scratch) cudaFreeHost(g->g_scratch);
+    g->g_scratch = nullptr;
+    g->g_scratch_cap = 0;
+    CK(cudaMallocHost(&g->g_scratch, bytes + 4096));
+    g->g_scratch_cap = bytes + 4096;
+}
 
 int set_prior(cafe_b200_ctx* g, const float* prior, int32_t n)
 {
@@ -1630,10 +1795,17 @@ int eval_base(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double*
 {
     if (!neg_lnl) { g->err = "null argument"; return CAFE_B200_ERR_ARG; }
     std::vector<double> neg(g->shards.size(), 0.0);
-    Out<double> fam(g, family_lnl, 1);
-    const int rc = each(g, [&](int i, cafe_b200_ctx* s) { return cafe_b200_eval_base(s, lambdas, n_lambda, &neg[i], fam.at(i)); });
-    if (rc == CAFE_B200_OK) { *neg_lnl = combine(neg); fam.finish(); }
-    return rc;
+    try {
+        reset_scratch(g, family_lnl ? (size_t)g->F * sizeof(double) + 256 : 0);
+        Out<double> fam(g, family_lnl, 1);
+        const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+            const int r = cafe_b200_eval_base(s, lambdas, n_lambda, &neg[i], fam.at(i));
+            if (r == CAFE_B200_OK && !std::isinf(neg[i])) fam.scatter(i);
+            return r;
+        });
+        if (rc == CAFE_B200_OK) *neg_lnl = combine(neg);
+        return rc;
+    } catch (const CudaError& e) { return fail(g, e); }
 }
 
 int eval_gamma(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
@@ -1644,17 +1816,24 @@ int eval_gamma(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double
     const size_t n = g->shards.size();
     std::vector<double> neg(n, 0.0);
     std::vector<int64_t> nf(n, 0);
-    Out<double> o_cat(g, cat_lk, n_cat), o_fam(g, family_lk, 1), o_post(g, posterior, n_cat);
-    Out<uint8_t> o_sig(g, significant, n_cat), o_fail(g, failed, 1);
-    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
-        return cafe_b200_eval_gamma(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, &neg[i], o_cat.at(i), o_fam.at(i), o_post.at(i),
-                                    o_sig.at(i), o_fail.at(i), &nf[i]);
-    });
-    if (rc != CAFE_B200_OK) return rc;
-    *neg_lnl = combine(neg);      // a shard with a failed family reports +inf, and so does the sum (gamma_core.cpp:216-225)
-    if (n_failed) { *n_failed = 0; for (int64_t v : nf) *n_failed += v; }
-    o_cat.finish(); o_fam.finish(); o_post.finish(); o_sig.finish(); o_fail.finish();
-    return rc;
+    try {
+        reset_scratch(g, (size_t)g->F * ((cat_lk ? n_cat * 8 : 0) + (family_lk ? 8 : 0) + (posterior ? n_cat * 8 : 0) + (significant ? n_cat : 0) +
+                                         (failed ? 1 : 0)) + 5 * 256);
+        Out<double> o_cat(g, cat_lk, n_cat), o_fam(g, family_lk, 1), o_post(g, posterior, n_cat);
+        Out<uint8_t> o_sig(g, significant, n_cat), o_fail(g, failed, 1);
+        const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
+            const int r = cafe_b200_eval_gamma(s, lambdas, n_lambda, alpha, multipliers, cat_probs, n_cat, &neg[i], o_cat.at(i), o_fam.at(i),
+                                               o_post.at(i), o_sig.at(i), o_fail.at(i), &nf[i]);
+            if (r == CAFE_B200_OK && !(std::isinf(neg[i]) && nf[i] == 0)) {     // (rejected before launch: nothing was written)
+                o_cat.scatter(i); o_fam.scatter(i); o_post.scatter(i); o_sig.scatter(i); o_fail.scatter(i);
+            }
+            return r;
+        });
+        if (rc != CAFE_B200_OK) return rc;
+        *neg_lnl = combine(neg);      // a shard with a failed family reports +inf, and so does the sum (gamma_core.cpp:216-225)
+        if (n_failed) { *n_failed = 0; for (int64_t v : nf) *n_failed += v; }
+        return rc;
+    } catch (const CudaError& e) { return fail(g, e); }
 }
 
 int enqueue_eval(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, double alpha, const double* multipliers, const double* cat_probs,
@@ -1720,13 +1899,16 @@ int reconstruct(cafe_b200_ctx* g, const double* lambdas, int32_t n_lambda, const
 {
     if (!states) { g->err = "bad argument"; return CAFE_B200_ERR_ARG; }
     const size_t K = n_cat > 0 ? n_cat : 1, nn = (size_t)g->n_nodes;
-    Out<int32_t> o_cat(g, cat_states, K * nn), o_st(g, states, nn);
-    Out<double> o_avg(g, averaged, nn);
-    const int rc = each(g, [&](int i, cafe_b200_ctx* s) {
-        return cafe_b200_reconstruct(s, lambdas, n_lambda, multipliers, cat_probs, n_cat, o_cat.at(i), o_st.at(i), o_avg.at(i));
-    });
-    if (rc == CAFE_B200_OK) { o_cat.finish(); o_st.finish(); o_avg.finish(); }
-    return rc;
+    try {
+        reset_scratch(g, (size_t)g->F * nn * ((cat_states ? K * 4 : 0) + 4 + (averaged ? 8 : 0)) + 3 * 256);
+        Out<int32_t> o_cat(g, cat_states, K * nn), o_st(g, states, nn);
+        Out<double> o_avg(g, averaged, nn);
+        return each(g, [&](int i, cafe_b200_ctx* s) {
+            const int r = cafe_b200_reconstruct(s, lambdas, n_lambda, multipliers, cat_probs, n_cat, o_cat.at(i), o_st.at(i), o_avg.at(i));
+            if (r == CAFE_B200_OK) { o_cat.scatter(i); o_st.scatter(i); o_avg.scatter(i); }
+            return r;
+        });
+    } catch (const CudaError& e) { return fail(g, e); }
 }
 
 }  // namespace group

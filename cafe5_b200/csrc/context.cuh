@@ -49,7 +49,13 @@ struct DevBuf {
         cap = 0;
         CK(cudaMalloc(&p, n * sizeof(T)));
         cap = n;
-        if (zero) CK(cudaMemset(p, 0, n * sizeof(T)));
+        if (zero) {
+            // cudaMemset runs on the legacy default stream, which the contexts' non-blocking streams do NOT wait for: without the
+            // synchronisation the zeros can land after a kernel on the context's stream has started writing the buffer (seen with
+            // several contexts on one device: whole shards of factor tables wiped during their first evaluation)
+            CK(cudaMemset(p, 0, n * sizeof(T)));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
     }
     void release()
     {
@@ -161,6 +167,18 @@ struct cafe_b200_ctx {
     // cafe_b200_create_bucketed: the shards are BUCKETS of families by largest count (own, smaller state space each) on one device;
     // order[shard_begin[b] + j] is the caller's index of family j of bucket b (empty: shards are contiguous blocks in caller order)
     std::vector<int64_t> order;
+    // page-locked scratch of a group whose shards are not contiguous in the caller's order: the shards write their outputs there
+    // and scatter them into the caller's arrays (each shard worker its own rows)
+    void* g_scratch = nullptr;
+    size_t g_scratch_cap = 0, g_scratch_used = 0;
+    void* take_scratch(size_t bytes)
+    {
+        bytes = (bytes + 255) / 256 * 256;
+        if (g_scratch_used + bytes > g_scratch_cap) return nullptr;
+        void* p = (char*)g_scratch + g_scratch_used;
+        g_scratch_used += bytes;
+        return p;
+    }
 
     int device = 0;
     int n_sms = 0;

@@ -336,6 +336,23 @@ class Context:
         return dict(launches=nl.value, matrices=nm.value, ms_matrices=a.value, ms_prune=b.value)
 
 
+def plan_shards(tree, counts, n_shards):
+    """(order[F], bounds[n_shards + 1]) of cafe_b200_plan_shards: families ordered by total count and cut into blocks of equal cost
+    under the subtree-pattern table plan.  Host-only."""
+    lib = _lib.load()
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    keep = (np.ascontiguousarray(tree.parent, dtype=np.int32), np.ascontiguousarray(tree.branch_length, dtype=np.float64),
+            np.ascontiguousarray(tree.leaf_col, dtype=np.int32), np.ascontiguousarray(tree.lambda_class, dtype=np.int32))
+    ct = _lib.CTree(tree.n_nodes, _lib.ip(keep[0]), _lib.dp(keep[1]), _lib.ip(keep[2]), _lib.ip(keep[3]))
+    order = np.zeros(counts.shape[0], dtype=np.int64)
+    bounds = np.zeros(int(n_shards) + 1, dtype=np.int64)
+    rc = lib.cafe_b200_plan_shards(C.byref(ct), _lib.ip(counts), counts.shape[0], counts.shape[1], int(n_shards),
+                                   order.ctypes.data_as(C.POINTER(C.c_int64)), bounds.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc:
+        raise CafeError("plan_shards: bad argument")
+    return order, bounds
+
+
 def discrete_gamma(n_cat, alpha):
     """(cat_probs, multipliers) from the library's C++ host implementation of get_gamma (cafe5_b200/host/discrete_gamma.hpp)."""
     lib = _lib.load()

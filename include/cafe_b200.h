@@ -67,7 +67,8 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
 
 /* The same model spread over several GPUs of one node from ONE host thread (the reference's only parallel axis is the
  * family loop, `#pragma omp parallel for` at src/base_model.cpp:69 and src/gamma_core.cpp:190): families are split into n_devices
- * contiguous shards, shard i lives on devices[i] with its own stream, every device regenerates the (small) matrices itself, and each
+ * shards (contiguous blocks of the caller's order; for large jobs clustered, work-balanced blocks, see cafe_b200_plan_shards), shard i
+ * lives on devices[i] with its own stream, every device regenerates the (small) matrices itself, and each
  * call below launches on all devices before it waits for any.  The only cross-device step is the final sum of base_model.cpp:95 /
  * gamma_core.cpp:233: the per-device partial sums {sum lnL, n_failed} (16 bytes each) are added on the host in device order, so a
  * score is bit-reproducible for a given device list.  Per-family outputs are written straight into the caller's buffers at the
@@ -95,6 +96,13 @@ int cafe_b200_create_bucketed(const cafe_b200_tree* tree, const int32_t* counts,
  * build_reference_list, src/base_model.cpp:27-51) through every node; here every distinct family, and a node whose subtree shows
  * few distinct patterns of leaf counts is computed once per PATTERN (its factor table) and gathered by the families that share it. */
 int cafe_b200_node_columns(const cafe_b200_ctx* ctx, int64_t* columns);
+
+/* How to cut a job into n_shards pieces for strong scaling (host-only; what cafe_b200_create_multi does for large jobs, exported for
+ * hosts that run one process per GPU).  order[n_families] receives the family indices ordered by total count (families with similar
+ * counts share the most subtree patterns), bounds[n_shards + 1] the cut points in that order, moved until every piece costs the same
+ * number of contraction columns under the subtree-pattern table plan: shard i prunes the families order[bounds[i] .. bounds[i+1]). */
+int cafe_b200_plan_shards(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species, int32_t n_shards,
+                          int64_t* order, int64_t* bounds);
 
 /* Number of device shards behind a context (1 for cafe_b200_create). */
 int32_t cafe_b200_n_devices(const cafe_b200_ctx* ctx);

@@ -158,6 +158,30 @@ def test_combine_partials_rejects_failures():
     assert dist.combine_partials([(1.5, 2), (2.0, 0)]) == (math.inf, 2)
 
 
+def test_plan_shards_is_a_balanced_partition(monkeypatch):
+    """cafe_b200_plan_shards (host-only): a permutation of the families ordered by total count, cut into n_shards non-empty
+    contiguous blocks whose cost under the subtree-pattern table plan is balanced (tables forced so that the small test job plans any)."""
+    from cafe5_b200.model import plan_shards
+    monkeypatch.setenv("CAFE_B200_TABLES", "force")
+    monkeypatch.setenv("CAFE_B200_TABLE_FRAC", "0.75")
+    rng = np.random.default_rng(12)
+    t = FlatTree("(((A:1,B:1):1,(C:1,D:1):1):1,((E:1,F:1):1,(G:1,H:1):1):1)")
+    F = 6000
+    size = rng.integers(1, 60, size=F)
+    counts = np.clip(size[:, None] + rng.integers(-2, 3, size=(F, 8)) * (size[:, None] > 20), 0, 80).astype(np.int32)   # large families vary more
+    for n_shards in (1, 3, 8):
+        order, bounds = plan_shards(t, counts, n_shards)
+        assert sorted(order.tolist()) == list(range(F))
+        assert bounds[0] == 0 and bounds[-1] == F and (np.diff(bounds) > 0).all()
+        tot = counts.sum(axis=1)[order]
+        assert (np.diff(tot) >= 0).all()                                   # ordered by total count
+    order, bounds = plan_shards(t, counts, 8)
+    sizes = np.diff(bounds)
+    assert sizes[0] > sizes[-2]                                            # blocks of small, repetitive families are longer
+    order, bounds = plan_shards(t, counts[:5], 8)                          # more shards than families
+    assert len(bounds) == 9 and bounds[5] == 5
+
+
 def test_abi_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "cafe_b200.h")).read()
     declared = sorted(set(re.findall(r"\b(cafe_b200_[a-z0-9_]+)\s*\(", header)))
