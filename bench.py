@@ -377,7 +377,9 @@ def run_ours(args):
     cpu_group = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank-dependent code path shows up as an abort after two minutes, not as a ten-minute hang
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
         cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not put a spinning kernel on a GPU
 
     def barrier():
@@ -530,7 +532,8 @@ def run_ours(args):
 
     # ---------------- weak-scaling side series: 125,000 families per GPU (round 1's workload) ----------------
     weak = None
-    if not args.no_weak and counts.shape[0] != WEAK_FAMILIES and counts.shape[0] > WEAK_FAMILIES:
+    # (the decision must not depend on the rank: the shards have different sizes and the block below contains collectives)
+    if not args.no_weak and int(np.diff(bounds).min()) > WEAK_FAMILIES:
         wctx = Context(tree, counts[:WEAK_FAMILIES], mfs, mrs, device=local)
         wctx.set_prior(prior)
         wstream = torch.cuda.ExternalStream(wctx.stream(), device=torch.device("cuda", local))
