@@ -1756,8 +1756,26 @@ struct Out {
     void scatter(int shard)
     {
         if (!tmp) return;
-        for (int64_t p = g->shard_begin[shard]; p < g->shard_begin[shard + 1]; ++p)
-            memcpy(user + (size_t)g->order[p] * width, tmp + (size_t)p * width, width * sizeof(T));
+        const int64_t b = g->shard_begin[shard], e = g->shard_begin[shard + 1];
+        const int64_t* __restrict__ ord = g->order.data();
+        const size_t bytes = width * sizeof(T);
+        if (bytes == 1) {
+            const uint8_t* s8 = (const uint8_t*)tmp; uint8_t* d8 = (uint8_t*)user;
+            for (int64_t p = b; p < e; ++p) d8[ord[p]] = s8[p];
+        } else if (bytes % 8 == 0 && bytes <= 64) {      // a family's row of doubles: word copies instead of a memcpy call per row
+            const size_t w = bytes / 8;
+            const uint64_t* s64 = (const uint64_t*)tmp; uint64_t* d64 = (uint64_t*)user;
+            for (int64_t p = b; p < e; ++p) {
+                const uint64_t* sp = s64 + (size_t)p * w; uint64_t* dp = d64 + (size_t)ord[p] * w;
+                for (size_t i = 0; i < w; ++i) dp[i] = sp[i];
+            }
+        } else if (bytes <= 8) {
+            const uint8_t* s8 = (const uint8_t*)tmp; uint8_t* d8 = (uint8_t*)user;
+            for (int64_t p = b; p < e; ++p)
+                for (size_t i = 0; i < bytes; ++i) d8[(size_t)ord[p] * bytes + i] = s8[(size_t)p * bytes + i];
+        } else {
+            for (int64_t p = b; p < e; ++p) memcpy(user + (size_t)ord[p] * width, tmp + (size_t)p * width, bytes);
+        }
     }
 };
 

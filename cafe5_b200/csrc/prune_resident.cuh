@@ -186,6 +186,7 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
         }
         const int32_t* mat_of = p.mat_of + (size_t)k * p.n_nodes;
         double acc[TMW][TNW][2];
+        int pf_id = -1;                         // table row this thread pulls into L2 for the next step's gathers (-1: none)
 
         for (int st = JOBS ? c_job : 0; st < (JOBS ? c_job + 1 : p.n_steps); ++st) {
             Step sp;
@@ -338,6 +339,57 @@ prune_resident_kernel(const PruneParams p, const int NS, const __grid_constant__
                     if (lane == 0) mbar_arrive(empty_bar + c_stage);
                     if (++c_stage == NS) { c_stage = 0; c_phase ^= 1u; }
                     if (!PRODUCE_FIRST && !MID) produce_one();
+                    // The table rows the NEXT step (or this CTA's next tile) gathers come from HBM: their ids are loaded early in this
+                    // contraction and the rows pulled into L2 from its middle, so that the staged bulk copy and the register gather
+                    // find them there.  Thread c of role r handles column c of the last (r = 0) / first (r = 1) child.
+                    if (sched.valid && (chunk == 1 || chunk == (n_chunks >> 1)) && tid < 2 * BN) {
+                        int nst = st + 1, ntile = tile, nk = k;
+                        int64_t ncol0 = col0, nU = U, nUs = U_stride;
+                        const int32_t* nids = ids;
+                        bool have = true;
+                        if (JOBS || nst == p.n_steps) {
+                            ntile += gridDim.x;
+                            have = ntile < n_tiles;
+                            if (have) {
+                                if (JOBS) {
+                                    int nj = c_job;
+                                    while (nj + 1 < sched.n_jobs && ntile >= job_word(nj + 1, 0)) ++nj;
+                                    const int local = ntile - job_word(nj, 0), ncol = job_word(nj, 1);
+                                    nst = nj;
+                                    nk = local / ncol;
+                                    ncol0 = (int64_t)(local % ncol) * BN;
+                                    nU = job_word(nj, 2);
+                                    nUs = job_word(nj, 3);
+                                    nids = p.counts_t + (((int64_t)job_word(nj, 5) << 32) | (uint32_t)job_word(nj, 4));
+                                } else {
+                                    nst = 0;
+                                    nk = ntile / p.n_col_tiles;
+                                    ncol0 = (int64_t)(ntile % p.n_col_tiles) * BN;
+                                }
+                            }
+                        }
+                        if (have) {
+                            const int nch = sched.w[nst * 9 + 3], cb = sched.w[nst * 9 + 4];
+                            const int role = tid / BN;
+                            const int ci = role == 0 ? nch - 1 : 0;
+                            if (nch > role && ci >= 0) {
+                                const int o = sched.off_children + (cb + ci) * 5;
+                                if (sched.w[o + 3] == 3) {                      // a table node
+                                    if (chunk == 1) {
+                                        int64_t u = ncol0 + (tid % BN);
+                                        if (u >= nU) u = nU - 1;
+                                        pf_id = nids[(size_t)sched.w[o + 1] * nUs + u];
+                                    } else if (pf_id >= 0) {
+                                        const char* row = reinterpret_cast<const char*>(
+                                            p.tables + ((size_t)sched.w[o + 2] * p.K + (size_t)nk * sched.w[o + 4] + pf_id) * p.LD);
+#pragma unroll
+                                        for (int b = 0; b < (BM * 8 + 127) / 128; ++b) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b * 128));
+                                        pf_id = -1;
+                                    }
+                                }
+                            }
+                        }
+                    }
                     if (PROBE && probe_out && probe_n < PROBE_CHUNKS) {
                         probe_out[probe_n * 4 + 0] = t_a;
                         probe_out[probe_n * 4 + 1] = t_b;

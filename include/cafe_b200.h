@@ -23,6 +23,11 @@
  *   - one context per host thread; a context is bound to one CUDA device (cafe_b200_create) or shards its families over
  *     several devices of the node (cafe_b200_create_multi).
  *   - there is no CPU fallback: create fails with CAFE_B200_ERR_CUDA when no device is usable.
+ *   - state-space limit: the default kernels hold the whole state space in one 208-row pass (max(max_family_size,
+ *     max_root_family_size) <= 207: every bundled data set, up to counts of ~165); larger spaces take the streamed-operand kernels (tested
+ *     up to max_family_size 720, where the reference switches to compute_node_probability_large_families at 1000,
+ *     src/probability.cpp:317-330); create returns CAFE_B200_ERR_RANGE once the narrowest Pupko tile no longer fits shared memory
+ *     (max_family_size beyond roughly 1,400).
  *
  * Tree layout: nodes in the reference's reverse level order (src/clade.cpp:69-100): children
  * precede parents, the root is the LAST node; the reference's descendant order of a node is

@@ -7,7 +7,7 @@ for v in "CAFE_B200_TABLES=0" "CAFE_B200_TABLE_FRAC=0.25" "CAFE_B200_TABLE_FRAC=
   env $v timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-fit 2> gpurun_out/bench.err | tee "gpurun_out/bench_tables_${v##*=}.json" | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('value %.0f e2e %.0f ms/step %.2f prune ms %.2f mat ms %.3f launches %d'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['ms_per_launch'],d['roofline']['matrix_gen']['ms_per_launch'],d['gpu_launches']), d['result'])
+print('value %.0f e2e %.0f ms/step %.2f prune ms %.2f mat ms %.3f launches %d'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['ms_per_step_kernel'],d['roofline']['matrix_gen']['ms_per_launch'],d['gpu_launches']), d['result'])
 "
   tail -3 gpurun_out/bench.err
 done
