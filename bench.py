@@ -380,7 +380,8 @@ def run_ours(args):
         import datetime
         # a short collective timeout: a rank-dependent code path shows up as an abort after two minutes, not as a ten-minute hang
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
-        cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not put a spinning kernel on a GPU
+        # host-side waits that must not put a spinning kernel on a GPU (rank 0 works alone for up to a minute at a time)
+        cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=900))
 
     def barrier():
         torch.cuda.synchronize()
@@ -514,17 +515,21 @@ def run_ours(args):
     if world > 1:
         multi_ms = None
         if rank == 0:
-            # every rank holds the same simulated table; the failing families were replaced shard by shard, so rebuild the job's
-            # table from the shards' healthy view: rank 0 repeats the (deterministic) replacement for every shard
-            parts = [drop_failing_families(args, tree, all_counts, mfs, mrs, order[bounds[r]:bounds[r + 1]], local)[0] for r in range(world)]
-            job = np.concatenate(parts)
-            mctx = Context(tree, job, mfs, mrs, devices=list(range(world)))
-            mctx.set_prior(prior)
-            multi_ms = e2e_loop(mctx, args.steps, False)
-            multi_U = mctx.unique_families()
-            mctx.close()
+            try:
+                # every rank holds the same simulated table; the failing families were replaced shard by shard, so rebuild the job's
+                # table from the shards' healthy view: rank 0 repeats the (deterministic) replacement for every shard
+                parts = [drop_failing_families(args, tree, all_counts, mfs, mrs, order[bounds[r]:bounds[r + 1]], local)[0] for r in range(world)]
+                job = np.concatenate(parts)
+                mctx = Context(tree, job, mfs, mrs, devices=list(range(world)))
+                mctx.set_prior(prior)
+                multi_ms = e2e_loop(mctx, args.steps, False)
+                multi_U = mctx.unique_families()
+                mctx.close()
+            except Exception as e:      # rank 0 must reach the barrier below whatever happens; e2e then stays the per-rank number
+                print("one-process e2e failed: %r" % (e,), file=sys.stderr, flush=True)
+                multi_ms = None
         dist.barrier(group=cpu_group)                 # the other ranks wait on the host: no kernel of theirs on the GPUs meanwhile
-        if rank == 0:
+        if rank == 0 and multi_ms is not None:
             e2e = {"value": multi_U / (multi_ms * 1e-3), "unit": "family-likelihood evals/s", "ms_per_step": multi_ms,
                    "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(args.families * d2h_per_family + 16 * world),
                    "what": "cafe_b200_create_multi: one host process drives all %d GPUs (what a CAFE5 process linked against the drop-in "

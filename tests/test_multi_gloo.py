@@ -132,3 +132,47 @@ def test_two_rank_sharded_fit_matches_single_rank():
     x, f, it = minimize(whole, [0.01, 1.0], 25)
     assert it == results[0][3]
     assert np.allclose(x, results[0][1], rtol=1e-9) and abs(f - results[0][2]) <= 1e-11 * f
+
+
+def _planned_worker(rank, world, port, out_queue):
+    """Shards from cafe_b200_plan_shards (families ordered by total count, unequal block sizes) instead of contiguous blocks."""
+    import torch.distributed as dist
+    from cafe5_b200.model import plan_shards
+    from oracle.pyoracle import OracleLib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["CAFE_B200_TABLES"] = "force"          # the planner balances table-plan cost; forced so that 41 families plan any
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = OracleLib()
+    o.set_threads(1)
+    tree = FlatTree(NEWICK)
+    counts = _counts()
+    order, bounds = plan_shards(tree, counts, world)
+    members = order[bounds[rank]:bounds[rank + 1]]
+    prior = fam.uniform_prior(45)
+    r = o.eval_gamma(tree, counts[members], 60, 45, prior, [0.01], [0.5, 1.5], [0.5, 0.5])
+    total, nfail = cdist.allreduce_score(r["neg_lnl"], r["n_failed"])
+    out_queue.put((rank, total, nfail, order.tolist(), bounds.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_planned_shards_score():
+    from oracle.pyoracle import OracleLib
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_planned_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][3:] == results[1][3:]                              # every rank computed the same plan
+    order, bounds = results[0][3], results[0][4]
+    assert sorted(order) == list(range(41)) and bounds[0] == 0 and bounds[-1] == 41 and 0 < bounds[1] < 41
+    assert results[0][1:3] == results[1][1:3]                            # and ends with the identical score
+    o = OracleLib()
+    want = o.eval_gamma(FlatTree(NEWICK), _counts(), 60, 45, fam.uniform_prior(45), [0.01], [0.5, 1.5], [0.5, 0.5])
+    assert results[0][2] == 0 and abs(results[0][1] - want["neg_lnl"]) <= 1e-12 * want["neg_lnl"]
