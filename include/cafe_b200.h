@@ -76,8 +76,9 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
  * lives on devices[i] with its own stream, every device regenerates the (small) matrices itself, and each
  * call below launches on all devices before it waits for any.  The only cross-device step is the final sum of base_model.cpp:95 /
  * gamma_core.cpp:233: the per-device partial sums {sum lnL, n_failed} (16 bytes each) are added on the host in device order, so a
- * score is bit-reproducible for a given device list.  Per-family outputs are written straight into the caller's buffers at the
- * shard's offset.  The returned handle is used with every other entry point of this header exactly like a single-device context
+ * score is bit-reproducible for a given device list.  Per-family outputs always arrive in the CALLER's family order: contiguous
+ * shards write straight into the caller's buffers at their offset, clustered shards go through page-locked scratch of the group and are
+ * scattered back by the shard's worker thread.  The returned handle is used with every other entry point of this header exactly like a single-device context
  * (simulate, get_matrix and the stream / stats hooks act on the first device).  n_devices == 1 is cafe_b200_create. */
 int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t* counts, int64_t n_families, int32_t n_species,
                            int32_t max_family_size, int32_t max_root_family_size, const int32_t* devices, int32_t n_devices,
