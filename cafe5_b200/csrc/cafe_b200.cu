@@ -1599,6 +1599,9 @@ extern "C" int cafe_b200_create_multi(const cafe_b200_tree* tree, const int32_t*
             create_error() = "shard planning failed";
             return CAFE_B200_ERR_ARG;
         }
+        // inside a shard the families keep the caller's relative order: the scatter of the per-family outputs then walks the caller's
+        // arrays front to back instead of hopping at random
+        for (int i = 0; i < n_shards; ++i) std::sort(g->order.begin() + g->shard_begin[i], g->order.begin() + g->shard_begin[i + 1]);
         packed.resize((size_t)n_families * n_species);
         for (int64_t p = 0; p < n_families; ++p)
             memcpy(&packed[(size_t)p * n_species], counts + (size_t)g->order[p] * n_species, n_species * sizeof(int32_t));
