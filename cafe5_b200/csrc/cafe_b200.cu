@@ -1536,6 +1536,7 @@ extern "C" int cafe_b200_plan_shards(const cafe_b200_tree* tree, const int32_t* 
                                      int32_t n_shards, int64_t* order, int64_t* bounds)
 {
     if (!tree || !counts || n_families <= 0 || n_species <= 0 || n_shards < 1 || !order || !bounds) return CAFE_B200_ERR_ARG;
+    for (int i = 0; i <= n_shards; ++i) bounds[i] = n_families;        // more shards than families: the extra shards are empty
     n_shards = (int32_t)std::min<int64_t>(n_shards, n_families);
     std::vector<int64_t> total((size_t)n_families, 0);
     for (int64_t f = 0; f < n_families; ++f)

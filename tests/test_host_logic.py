@@ -179,7 +179,7 @@ def test_plan_shards_is_a_balanced_partition(monkeypatch):
     sizes = np.diff(bounds)
     assert sizes[0] > sizes[-2]                                            # blocks of small, repetitive families are longer
     order, bounds = plan_shards(t, counts[:5], 8)                          # more shards than families
-    assert len(bounds) == 9 and bounds[5] == 5
+    assert len(bounds) == 9 and bounds[5] == 5 and (bounds[5:] == 5).all()
 
 
 def test_abi_library_exports_every_declared_symbol():
