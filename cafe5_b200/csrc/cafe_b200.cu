@@ -1757,10 +1757,23 @@ struct Out {
         }
     }
     T* at(int shard) { return !user ? nullptr : (tmp ? tmp : user) + (size_t)g->shard_begin[shard] * width; }
+    // rows [b, e) of the scratch -> the caller's order.  Called by the shard's worker; large shards split the rows over a few helper
+    // threads (the copy is latency-bound: one thread moves ~5 GB/s of 1 ... 32-byte rows)
     void scatter(int shard)
     {
         if (!tmp) return;
         const int64_t b = g->shard_begin[shard], e = g->shard_begin[shard + 1];
+        const int64_t rows = e - b;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int helpers = (int)std::min<int64_t>(std::max<int64_t>(1, (int64_t)hw / (int64_t)g->shards.size()), std::min<int64_t>(8, rows / 32768));
+        if (helpers <= 1) { scatter_rows(b, e); return; }
+        std::vector<std::thread> th;
+        for (int t = 1; t < helpers; ++t) th.emplace_back([=] { scatter_rows(b + rows * t / helpers, b + rows * (t + 1) / helpers); });
+        scatter_rows(b, b + rows / helpers);
+        for (auto& x : th) x.join();
+    }
+    void scatter_rows(int64_t b, int64_t e)
+    {
         const int64_t* __restrict__ ord = g->order.data();
         const size_t bytes = width * sizeof(T);
         if (bytes == 1) {
