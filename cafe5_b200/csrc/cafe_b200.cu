@@ -953,6 +953,26 @@ int cafe_b200_create(const cafe_b200_tree* tree, const int32_t* counts, int64_t 
         }
         c->U = (int64_t)uniq.size();
         c->U_stride = (c->U + 63) / 64 * 64;
+        // Column order of the distinct families: by total count (stable), not by first appearance.  A family's values do not depend on
+        // its column, but a tile of 64 neighbouring columns then holds families of similar size: their leaf gathers hit the same few
+        // matrix rows, the table plan numbers the patterns of a node in nearly sorted order (ids are given in column order), and
+        // neighbouring columns gather neighbouring table rows.  CAFE_B200_SORT=0 keeps the order of first appearance.
+        {
+            const char* e = std::getenv("CAFE_B200_SORT");
+            if (!(e && std::strcmp(e, "0") == 0) && c->U > 1) {
+                std::vector<int64_t> total((size_t)c->U, 0), rank((size_t)c->U), by((size_t)c->U);
+                for (int64_t u = 0; u < c->U; ++u) {
+                    const int32_t* row = counts + (size_t)uniq[u] * n_species;
+                    for (int j = 0; j < n_leaves; ++j) total[u] += row[c->leaf_col[leaf_nodes[j]]];
+                    by[u] = u;
+                }
+                std::stable_sort(by.begin(), by.end(), [&](int64_t a, int64_t b) { return total[a] < total[b]; });
+                std::vector<int64_t> sorted((size_t)c->U);
+                for (int64_t pos = 0; pos < c->U; ++pos) { sorted[pos] = uniq[by[pos]]; rank[by[pos]] = pos; }
+                uniq.swap(sorted);
+                for (int64_t f = 0; f < n_families; ++f) c->f2u[f] = rank[c->f2u[f]];
+            }
+        }
         std::vector<int32_t> counts_t((size_t)n_leaves * c->U_stride, 0);
         for (int64_t u = 0; u < c->U; ++u) {
             const int32_t* row = counts + (size_t)uniq[u] * n_species;
