@@ -203,6 +203,44 @@ def test_create_fails_loudly_without_a_gpu():
         Context(t, np.array([[1, 2]], dtype=np.int32), 56, 8)
 
 
+def test_group_constructors_reject_bad_arguments_before_touching_a_device():
+    """cafe_b200_create_multi / cafe_b200_create_bucketed: hard errors are status codes with text (include/cafe_b200.h), the handle
+    stays NULL, and without a GPU a well-formed call fails with the CUDA status -- never a CPU computation."""
+    import torch
+    lib = _lib.load()
+    t = FlatTree("((A:1,B:1):1,C:2);")
+    keep = (np.ascontiguousarray(t.parent, dtype=np.int32), np.ascontiguousarray(t.branch_length, dtype=np.float64),
+            np.ascontiguousarray(t.leaf_col, dtype=np.int32), np.ascontiguousarray(t.lambda_class, dtype=np.int32))
+    ct = _lib.CTree(t.n_nodes, _lib.ip(keep[0]), _lib.dp(keep[1]), _lib.ip(keep[2]), _lib.ip(keep[3]))
+    counts = np.array([[1, 2, 3], [4, 0, 2]], dtype=np.int32)
+    devs = np.array([0, 0], dtype=np.int32)
+    ceilings = np.array([16, 32], dtype=np.int32)
+
+    def multi(counts_p, F, devices_p, n_dev):
+        h = ctypes.c_void_p(1)
+        rc = lib.cafe_b200_create_multi(ctypes.byref(ct), counts_p, F, 3, 40, 20, devices_p, n_dev, ctypes.byref(h))
+        return rc, h.value, lib.cafe_b200_last_error(None).decode()
+
+    def bucketed(counts_p, F, ceil_p, n_ceil, mfs=40):
+        h = ctypes.c_void_p(1)
+        rc = lib.cafe_b200_create_bucketed(ctypes.byref(ct), counts_p, F, 3, mfs, 20, ceil_p, n_ceil, 0, ctypes.byref(h))
+        return rc, h.value, lib.cafe_b200_last_error(None).decode()
+
+    ERR_ARG, ERR_RANGE = 1, 3
+    for rc, h, msg in (multi(_lib.ip(counts), 2, None, 2), multi(_lib.ip(counts), 2, _lib.ip(devs), 0),
+                       multi(None, 2, _lib.ip(devs), 2), multi(_lib.ip(counts), 0, _lib.ip(devs), 2),
+                       bucketed(_lib.ip(counts), 2, None, 2), bucketed(_lib.ip(counts), 2, _lib.ip(ceilings), 0),
+                       bucketed(None, 2, _lib.ip(ceilings), 2)):
+        assert rc == ERR_ARG and h is None and msg
+    rc, h, msg = bucketed(_lib.ip(counts), 2, _lib.ip(np.array([0, 16], dtype=np.int32)), 2)
+    assert rc == ERR_ARG and h is None and "positive" in msg
+    rc, h, msg = bucketed(_lib.ip(counts), 2, _lib.ip(ceilings), 2, mfs=3)           # count 4 > max_family_size 3
+    assert rc == ERR_RANGE and h is None and "max_family_size" in msg
+    if not torch.cuda.is_available():
+        for rc, h, msg in (multi(_lib.ip(counts), 2, _lib.ip(devs), 2), bucketed(_lib.ip(counts), 2, _lib.ip(ceilings), 2)):
+            assert rc != 0 and h is None and msg
+
+
 # ---- C++ host driver pieces of libcafe_b200.so that need no GPU (cafe5_b200/host/) ------------------------------
 
 def test_cpp_discrete_gamma_matches_python_and_reference(ref):
