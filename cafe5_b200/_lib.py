@@ -18,7 +18,7 @@ SYMBOLS = [
     "cafe_b200_fetch_result", "cafe_b200_stream", "cafe_b200_last_stats", "cafe_b200_unique_families",
     "cafe_b200_measure_fp64_peak", "cafe_b200_describe", "cafe_b200_discrete_gamma", "cafe_b200_minimize", "cafe_b200_fit", "cafe_b200_simulate", "cafe_b200_pvalues", "cafe_b200_io_last_error", "cafe_b200_io_parse_tree", "cafe_b200_io_read_families",
     "cafe_b200_io_read_error_model", "cafe_b200_io_derive_sizes", "cafe_b200_io_format_results", "cafe_b200_io_format_family_likelihoods", "cafe_b200_io_format_reconstruction", "cafe_b200_branch_probabilities",
-    "cafe_b200_create_multi", "cafe_b200_create_bucketed", "cafe_b200_plan_shards", "cafe_b200_n_devices", "cafe_b200_node_columns", "cafe_b200_result_device", "cafe_b200_io_make_prior",
+    "cafe_b200_create_multi", "cafe_b200_create_bucketed", "cafe_b200_plan_shards", "cafe_b200_n_devices", "cafe_b200_node_columns", "cafe_b200_result_device", "cafe_b200_io_make_prior", "cafe_b200_fit_poisson_prior",
     "cafe_b200_host_alloc", "cafe_b200_host_free", "cafe_b200_debug_read_probe", "cafe_b200_io_format_report", "cafe_b200_io_format_simulation", "cafe_b200_io_format_error_model",
 ]
 

@@ -20,7 +20,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <algorithm>
+#include <cctype>
 #include <random>
+#include <string>
 #include <vector>
 
 namespace {
@@ -118,6 +121,70 @@ extern "C" int cafe_b200_minimize(double (*objective)(const double*, void*), voi
     cafe_b200_host::NelderMeadResult r = nm.minimize(x0);
     std::memcpy(x_out, r.x.data(), n * sizeof(double));
     if (f_out) *f_out = r.f;
+    if (iterations) *iterations = r.iterations;
+    return CAFE_B200_OK;
+}
+
+// `-p` without a value: the Poisson mean of the root prior estimated from the gene families themselves
+// (root_equilibrium_distribution(gene_families, num_values), src/root_equilibrium_distribution.cpp:42-54; poisson_scorer,
+// src/poisson.cpp:21-78).  Every positive leaf count c contributes log pdf(c - 1; lambda), pdf(x; l) = exp(x log l - lgamma(x + 1) - l);
+// terms whose pdf is 0, inf or NaN are skipped; lambda < 0 scores +inf.  The terms are added family by family, and inside a family in
+// the order of the reference's species map (names compared case-insensitively) when the names are given, so that the sum -- and with
+// it the simplex trajectory -- is the reference's to the last bit.  Start: one uniform(0, 1) draw of the seeded engine, one retry
+// (optimizer::get_initial_guesses).  Host only.
+extern "C" int cafe_b200_fit_poisson_prior(const int32_t* counts, int64_t n_families, int32_t n_species, const char* species, uint32_t seed,
+                                           double* poisson_lambda, double* neg_lnl, int32_t* iterations)
+{
+    if (!counts || n_families < 1 || n_species < 1 || !poisson_lambda) return CAFE_B200_ERR_ARG;
+    std::vector<int> order(n_species);
+    for (int j = 0; j < n_species; ++j) order[j] = j;
+    if (species && *species) {
+        std::vector<std::string> names(1);
+        for (const char* c = species; *c; ++c) {
+            if (*c == '\t') names.emplace_back();
+            else names.back().push_back((char)std::tolower((unsigned char)*c));
+        }
+        if ((int)names.size() != n_species) return CAFE_B200_ERR_ARG;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {   // ci_less, src/gene_family.h:10-25
+            return std::lexicographical_compare(names[a].begin(), names[a].end(), names[b].begin(), names[b].end(),
+                                                [](char x, char y) { return (unsigned char)x < (unsigned char)y; });
+        });
+    }
+    std::vector<int> sizes;                    // poisson_scorer::leaf_family_sizes
+    for (int64_t f = 0; f < n_families; ++f)
+        for (int j = 0; j < n_species; ++j) {
+            const int32_t c = counts[(size_t)f * n_species + order[j]];
+            if (c > 0) sizes.push_back(c - 1);
+        }
+    auto score = [&](const double* v) {
+        const double lambda = v[0];
+        if (lambda < 0) return std::numeric_limits<double>::infinity();
+        double sum = 0.0;
+        for (int sz : sizes) {
+            const double ll = std::exp(sz * std::log(lambda) - std::lgamma((double)(sz + 1)) - lambda);
+            if (std::isnan(ll) || std::isinf(ll) || ll == 0) continue;
+            sum += std::log(ll);
+        }
+        return -sum;
+    };
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<double> distribution(0.0, 1.0);
+    double start = distribution(engine);
+    double first = score(&start);
+    for (int attempt = 0; std::isinf(first) && attempt < 1; ++attempt) {
+        start = distribution(engine);
+        first = score(&start);
+    }
+    if (std::isinf(first)) {                   // OptimizerInitializationFailure
+        *poisson_lambda = start;
+        if (neg_lnl) *neg_lnl = first;
+        if (iterations) *iterations = 0;
+        return CAFE_B200_ERR_STATE;
+    }
+    NelderMead nm(score, 1, NelderMeadOptions());
+    const NelderMeadResult r = nm.minimize(&start);
+    *poisson_lambda = r.x[0];
+    if (neg_lnl) *neg_lnl = r.f;
     if (iterations) *iterations = r.iterations;
     return CAFE_B200_OK;
 }

@@ -53,6 +53,20 @@ def read_error_model(path, rows_cap=100000):
     return probs[:rows.value].copy(), mx.value
 
 
+def fit_poisson_prior(counts, species=None, seed=10):
+    """`-p` without a value: (poisson_lambda, -lnL, iterations) of the reference's poisson_scorer over the positive leaf counts."""
+    L = _lib.load()
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    lam, neg, it = C.c_double(), C.c_double(), C.c_int32()
+    L.cafe_b200_fit_poisson_prior.argtypes = [C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.c_char_p, C.c_uint32, C.POINTER(C.c_double),
+                                              C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    sp = None if species is None else "\t".join(species).encode()
+    rc = L.cafe_b200_fit_poisson_prior(_lib.ip(counts), counts.shape[0], counts.shape[1], sp, int(seed), C.byref(lam), C.byref(neg), C.byref(it))
+    if rc:
+        raise RuntimeError("cafe_b200_fit_poisson_prior: status %d" % rc)
+    return lam.value, neg.value, it.value
+
+
 def make_prior(kind, num_values=0, poisson_lambda=0.0, rootdist_path=None):
     """float32 prior table built by the library as the reference builds it: kind 'uniform' | 'rootdist' | 'poisson'."""
     L = _lib.load()

@@ -247,6 +247,18 @@ int cafe_b200_io_read_error_model(const char* path, double* probs, int32_t rows_
 int cafe_b200_io_make_prior(int32_t kind, double poisson_lambda, const char* rootdist_path, int32_t num_values, float* prior, int32_t cap,
                             int32_t* n);
 
+/* `-p` without a value (user_data::create_prior, src/user_data.cpp:193-197): the Poisson mean of the root prior estimated from the gene
+ * families -- the reference's poisson_scorer (src/poisson.cpp:40-78: every positive leaf count c contributes log pdf(c - 1; lambda))
+ * minimised by the same simplex search from a seeded uniform(0, 1) start (root_equilibrium_distribution(gene_families, num_values),
+ * src/root_equilibrium_distribution.cpp:42-54).  counts[n_families x n_species]; species: the tab-joined column names as
+ * cafe_b200_io_read_families returns them (the reference adds a family's terms in the order of its case-insensitive species map; NULL
+ * or "": column order -- same minimum, the sum may differ in the last bits).  The table is then
+ * cafe_b200_io_make_prior(2, *poisson_lambda, NULL, (int)(max_root_family_size * 0.8), ...).  Returns CAFE_B200_ERR_STATE when no
+ * start point has a finite score (OptimizerInitializationFailure).  The reference draws the start from its one process-wide engine
+ * before any model is fitted; a host reproducing a whole `-p` run seeds this call first.  Host only. */
+int cafe_b200_fit_poisson_prior(const int32_t* counts, int64_t n_families, int32_t n_species, const char* species, uint32_t seed,
+                                double* poisson_lambda, double* neg_lnl, int32_t* iterations);
+
 /* max_family_size / max_root_family_size from the count table (src/user_data.cpp:40-48, floors src/user_data.h:26-27). */
 int cafe_b200_io_derive_sizes(const int32_t* counts, int64_t n, int32_t* max_family_size, int32_t* max_root_family_size);
 

@@ -310,6 +310,18 @@ class RefLib:
                                              len(sizes) if rootdist else 0, int(num_values), _fp(out), cap, C.byref(tl)))
         return out[:tl.value].copy(), out
 
+    def fit_poisson_prior(self, species, counts, seed=10, num_values=100, cap=512):
+        """The reference's `-p` without a value: (poisson_lambda, score, iterations, float32 prior table) from its poisson_scorer,
+        optimizer and root_equilibrium_distribution(gene_families, num_values)."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        lam, score, it, tl = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        out = np.zeros(cap, dtype=np.float32)
+        self.lib.ref_fit_poisson_prior.argtypes = [C.c_char_p, c_ip, C.c_long, C.c_uint, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                   c_ip, C.POINTER(C.c_float), C.c_int, c_ip]
+        self._check(self.lib.ref_fit_poisson_prior("\t".join(species).encode(), _ip(counts), counts.shape[0], int(seed), int(num_values),
+                                                   C.byref(lam), C.byref(score), C.byref(it), _fp(out), cap, C.byref(tl)))
+        return lam.value, score.value, it.value, out[:tl.value].copy()
+
     def set_threads(self, n):
         self.lib.ref_set_threads(n)
 

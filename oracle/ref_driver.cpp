@@ -49,6 +49,7 @@
 #include "optimizer.h"
 #include "newick_ape_loader.h"
 #include "optimizer_scorer.h"
+#include "poisson.h"
 
 #include "ref_optimize.hpp"
 
@@ -201,6 +202,40 @@ int ref_prior_table(int kind, double poisson_lambda, const int* sizes, const int
         } else p.reset(new root_equilibrium_distribution(poisson_lambda, (size_t)num_values));
         for (int j = 0; j < cap; ++j) out[j] = p->compute(j);
         if (table_len) *table_len = (int)p->_frequency_percentage.size();
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// `-p` without a value: the reference estimates the Poisson mean of the root prior from the gene families
+// (root_equilibrium_distribution(gene_families, num_values), src/root_equilibrium_distribution.cpp:42-54).  That constructor keeps
+// neither the fitted mean nor the score, so its three statements are run here on the reference's own poisson_scorer and optimizer
+// (seeded randomizer_engine), and the constructor itself builds the table that is returned.
+int ref_fit_poisson_prior(const char* species, const int* counts, long F, unsigned seed, int num_values, double* poisson_lambda,
+                          double* score, int* iterations, float* table, int cap, int* table_len)
+{
+    ensure_init();
+    try {
+        auto sp = split(species, '\t');
+        std::vector<gene_family> fams(F);
+        for (long f = 0; f < F; ++f) {
+            fams[f].set_id(std::to_string(f));
+            for (size_t j = 0; j < sp.size(); ++j) fams[f].set_species_size(sp[j], counts[f * (long)sp.size() + (long)j]);
+        }
+        randomizer_engine.seed(seed);
+        poisson_scorer scorer(fams);
+        optimizer opt(&scorer);
+        opt.quiet = true;
+        optimizer_parameters params;
+        auto result = opt.optimize(params);
+        *poisson_lambda = result.values[0];
+        *score = result.score;
+        *iterations = result.num_iterations;
+        if (table) {
+            randomizer_engine.seed(seed);
+            root_equilibrium_distribution prior(fams, (size_t)num_values);
+            for (int j = 0; j < cap; ++j) table[j] = prior.compute(j);
+            if (table_len) *table_len = (int)prior._frequency_percentage.size();
+        }
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -117,6 +117,46 @@ def test_prior_tables_match_the_reference_constructors(ref, golden, tmp_path):
     assert np.array_equal(fam.rootdist_prior(rd), g["mammals_rootdist_prior"])
 
 
+def test_poisson_prior_estimated_from_the_families(golden):
+    """`-p` without a value (src/user_data.cpp:193-197): cafe_b200_fit_poisson_prior restates the reference's poisson_scorer
+    (src/poisson.cpp:40-78) under the host driver's simplex search.  With the reference present: the same fitted mean, score and
+    iteration count to the last bit for several seeds (the terms are added in the order of the reference's case-insensitive species
+    map), and the same prior table as root_equilibrium_distribution(gene_families, num_values).  Always: the committed answers of that
+    comparison."""
+    from cafe5_b200 import io_cpp
+    from oracle import pyoracle
+    known = {"mammals": (0.7823844312347201, 230742.16544235396, 38), "hymenoptera": (0.17864856014870018, 50673.78984391159, 25)}
+    for name, (lam, score, iters) in known.items():
+        g = golden[name]
+        species = [str(x) for x in g["species"]]
+        got = io_cpp.fit_poisson_prior(g["counts"], species, seed=10)
+        assert abs(got[0] - lam) <= 1e-12 * lam and abs(got[1] - score) <= 1e-12 * score and got[2] == iters
+        shuffled = io_cpp.fit_poisson_prior(g["counts"][:, ::-1], species[::-1], seed=10)      # column order does not matter with names
+        assert shuffled == got
+    if not pyoracle.have_ref():
+        return
+    ref = pyoracle.RefLib()
+    for name in known:
+        g = golden[name]
+        species = [str(x) for x in g["species"]]
+        num_values = int(int(g["max_root_family_size"]) * 0.8)
+        for seed in (10, 3, 77):
+            lam, score, iters, table = ref.fit_poisson_prior(species, g["counts"], seed=seed, num_values=num_values)
+            assert io_cpp.fit_poisson_prior(g["counts"], species, seed=seed) == (lam, score, iters), (name, seed)
+            assert np.array_equal(io_cpp.make_prior("poisson", num_values, lam), table)
+    # a table whose only counts are 0 has no terms: every start scores 0, the search ends where it started -- like the reference
+    species = ["a", "B", "c"]
+    zeros = np.zeros((4, 3), dtype=np.int32)
+    assert io_cpp.fit_poisson_prior(zeros, species, seed=5)[:2] == ref.fit_poisson_prior(species, zeros, seed=5, num_values=10)[:2]
+    # mixed-case names: the reference's map orders them case-insensitively
+    rng = np.random.default_rng(8)
+    species = ["zeta", "Alpha", "beta", "GAMMA", "delta"]
+    counts = rng.integers(0, 40, size=(300, 5)).astype(np.int32)
+    for seed in (1, 2):
+        lam, score, iters, _ = ref.fit_poisson_prior(species, counts, seed=seed, num_values=30)
+        assert io_cpp.fit_poisson_prior(counts, species, seed=seed) == (lam, score, iters)
+
+
 def test_error_model_file_and_epsilon_table(tmp_path):
     p = tmp_path / "em.txt"
     p.write_text("maxcnt: 20\ncntdiff -1 0 1\n0 0.0 0.8 0.2\n1 0.2 0.6 0.2\n20 0.2 0.6 0.2\n")
